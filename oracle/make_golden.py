@@ -1,0 +1,133 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference imported from /root/reference.
+
+Run here (the container that has /root/reference):   python -m oracle.make_golden
+The reference cannot travel to the GPU box, so its outputs are committed as small fixtures.
+Inputs are re-derived in the tests from the seeds stored in each file; weights come from
+oracle/weights.py (deterministic) and their fingerprint is stored so a silent RNG difference
+between machines is detected instead of producing a bogus parity failure.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims, weights  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def est_inputs(seed, R, T, lens):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(R, 80, T, generator=g)
+    mu = torch.randn(R, 80, T, generator=g)
+    spks = torch.randn(R, 80, generator=g)
+    cond = torch.randn(R, 80, T, generator=g) * 0.3
+    t = torch.rand(R, generator=g)
+    mask = torch.zeros(R, 1, T)
+    for i, l in enumerate(lens):
+        mask[i, 0, :l] = 1
+    return x, mask, mu, t, spks, cond
+
+
+def cfm_inputs(seed, T):
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.randn(1, 80, T, generator=g)
+    spks = torch.randn(1, 80, generator=g)
+    return mu, spks
+
+
+def hift_mel(seed, B, T):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 80, T, generator=g) * 2 - 5
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.manual_seed(0)
+
+    # ---------------- estimator / CFM ----------------
+    cfm = ref_shims.build_reference_cfm()
+    sd = weights.make_estimator_state_dict()
+    cfm.load_state_dict(sd, strict=True)
+    cs = weights.checksum(sd)
+    with torch.no_grad():
+        lens = [37, 20, 29]
+        x, mask, mu, t, spks, cond = est_inputs(5, 3, 37, lens)
+        v = cfm.estimator(x, mask, mu, t, spks, cond)
+        np.savez_compressed(os.path.join(OUT, "estimator_fwd.npz"), seed=5, R=3, T=37, lens=np.array(lens),
+                            out=v.numpy(), weight_checksum=np.array(cs))
+        for name, seed, T, n in (("cfm_T50_n10", 7, 50, 10), ("cfm_T33_n4", 8, 33, 4)):
+            mu, spks = cfm_inputs(seed, T)
+            mel, _ = cfm(mu, torch.ones(1, 1, T), n, 1.0, spks, torch.zeros(1, 80, T))
+            np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, T=T, n_timesteps=n, out=mel.numpy(),
+                                weight_checksum=np.array(cs))
+        # with a prompt-style non-zero cond
+        mu, spks = cfm_inputs(9, 40)
+        g = torch.Generator().manual_seed(90)
+        cond = torch.zeros(1, 80, 40)
+        cond[:, :, :12] = torch.randn(1, 80, 12, generator=g)
+        mel, _ = cfm(mu, torch.ones(1, 1, 40), 5, 0.8, spks, cond)
+        np.savez_compressed(os.path.join(OUT, "cfm_T40_n5_cond.npz"), seed=9, T=40, n_timesteps=5, temperature=0.8,
+                            out=mel.numpy(), weight_checksum=np.array(cs))
+    del cfm
+
+    # ---------------- HiFT ----------------
+    hift = ref_shims.build_reference_hift()
+    for tag, f0b in (("unvoiced", None), ("voiced", 200.0)):
+        sdh = weights.make_hift_state_dict(f0_bias=f0b)
+        hift.load_state_dict(sdh, strict=True)
+        csh = weights.checksum(sdh)
+        B, T = 2, 30
+        mel = hift_mel(3, B, T)
+        with torch.no_grad():
+            f0 = hift.f0_predictor(mel)
+            torch.manual_seed(11)
+            wav, s = hift.inference(mel)
+            wav_d = hift.decode(mel, s)
+            sr, si = hift._stft(s.squeeze(1))
+        np.savez_compressed(os.path.join(OUT, f"hift_{tag}.npz"), seed=3, B=B, T=T, rng_seed=11,
+                            f0=f0.numpy(), s=s.numpy().astype(np.float32), wav_inference=wav.numpy(),
+                            wav_decode=wav_d.numpy(), s_stft=torch.cat([sr, si], 1).numpy(),
+                            weight_checksum=np.array(csh))
+    del hift
+
+    # ---------------- integer length / alignment code ----------------
+    ref_shims.install()
+    from jyutvoice.utils.model import sequence_mask, generate_path
+    from jyutvoice.utils.mask import make_pad_mask
+    cases = {}
+    g = torch.Generator().manual_seed(21)
+    for ci, (B, Tx, ls) in enumerate([(1, 7, 1.0), (3, 11, 1.0), (2, 9, 3.0), (2, 5, 0.5), (1, 1, 1.0)]):
+        logw = torch.randn(B, 1, Tx, generator=g) * 0.8 + 0.3
+        x_lengths = torch.randint(1, Tx + 1, (B,), generator=g)
+        x_lengths[0] = Tx
+        x_mask = sequence_mask(x_lengths, Tx).unsqueeze(1).float()
+        # jyutvoice_tts.py:184-196
+        w = torch.exp(logw) * x_mask
+        w_ceil = torch.ceil(w) * ls
+        y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+        y_max = y_lengths.max()
+        y_mask = sequence_mask(y_lengths, y_max).unsqueeze(1).to(x_mask.dtype)
+        attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
+        attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1)).unsqueeze(1)
+        cases[f"c{ci}_logw"] = logw.numpy()
+        cases[f"c{ci}_x_lengths"] = x_lengths.numpy()
+        cases[f"c{ci}_length_scale"] = np.float32(ls)
+        cases[f"c{ci}_y_lengths"] = y_lengths.numpy()
+        cases[f"c{ci}_attn"] = attn.numpy()
+        cases[f"c{ci}_pad_mask"] = make_pad_mask(y_lengths).numpy()
+        cases[f"c{ci}_y_mask"] = y_mask.numpy()
+    cases["n_cases"] = 5
+    np.savez_compressed(os.path.join(OUT, "lengths.npz"), **cases)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
