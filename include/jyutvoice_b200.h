@@ -1,0 +1,121 @@
+/*
+ * jyutvoice_b200 — C-ABI of the B200-native CFM + HiFT hot path.
+ *
+ * The reference (indiejoseph/JyutVoice) is pure Python/PyTorch and has no FFI; the one seam it
+ * offers for swapping the estimator is the raw-pointer engine contract in
+ * jyutvoice/flow/flow_matching.py:267-297 (six device pointers x, mask, mu, t, spks, cond, result
+ * written on the caller's CUDA stream).  This header is what a binding for that seam, and for
+ * HiFTGenerator.inference/decode, calls.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 (JV_OK) or a negative JV_ERR_* code; jv_last_error() gives the text
+ *     (thread-local).  No exception crosses the ABI.
+ *   - "dev" pointers are device memory on the handle's device; "host" pointers are host memory.
+ *   - all tensors are dense, row-major, float32 unless noted; lens are int32 on the host.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised, except
+ *     where noted (set_weight / finalize synchronise the device).
+ *   - the caller owns every buffer, including the workspace arena sized by *_workspace_bytes().
+ *   - a handle is bound to one device and must not be used from two threads at once.
+ *   - precision: JV_PREC_FP32 computes every contraction in fp32 FFMA (the <=1e-3 / >=60 dB mode);
+ *     JV_PREC_BF16 runs contractions on tcgen05 tensor cores with bf16 operands, fp32 accumulation,
+ *     fp32 normalisation statistics and an fp32 residual stream.
+ */
+#ifndef JYUTVOICE_B200_H
+#define JYUTVOICE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JV_OK 0
+#define JV_ERR_INVALID (-1)   /* bad argument (maps to ValueError) */
+#define JV_ERR_CUDA (-2)      /* CUDA runtime / driver failure (RuntimeError) */
+#define JV_ERR_STATE (-3)     /* handle not finalised, missing weights, workspace too small */
+
+#define JV_PREC_FP32 0
+#define JV_PREC_BF16 1
+
+typedef struct jv_estimator jv_estimator;
+typedef struct jv_hift jv_hift;
+
+int jv_version(void);
+const char* jv_last_error(void);
+/* Number of kernel launches this library has enqueued in this process (bench.py's gpu_launches). */
+uint64_t jv_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Estimator = CausalConditionalDecoder (jyutvoice/flow/decoder.py:798-1018) with the
+ * configs/base.yaml:88-99 hyper-parameters, plus the Euler/CFG solver around it
+ * (ConditionalCFM.solve_euler, flow_matching.py:215-265).
+ * ------------------------------------------------------------------------------------------ */
+int jv_estimator_create(int device, int precision, jv_estimator** out);
+void jv_estimator_destroy(jv_estimator* h);
+/* Replaces nn.Module.load_state_dict for `decoder.estimator.*`: `key` is the reference's
+ * state_dict key without the "estimator." prefix (e.g. "mid_blocks.3.1.0.attn1.to_q.weight");
+ * `data` may be host or device fp32; `shape` is checked against the architecture. */
+int jv_estimator_set_weight(jv_estimator* h, const char* key, const float* data, const int64_t* shape, int ndim);
+/* Fails (JV_ERR_STATE, listing the first missing key) unless all 910 tensors were set. */
+int jv_estimator_finalize(jv_estimator* h);
+
+/* Workspace for B utterances (R = 2B estimator rows with CFG) of the given lengths. */
+size_t jv_cfm_workspace_bytes(const jv_estimator* h, int n_rows, const int32_t* lens_host);
+
+/* One estimator evaluation, the reference's forward(x, mask, mu, t, spks, cond) (decoder.py:917):
+ * x, mu, cond dev [R,80,Tmax]; spks dev [R,80]; t host [R]; mask is implied by lens (prefix masks,
+ * which is all the reference ever builds: jyutvoice_tts.py:225,229).  cond / spks may be NULL
+ * (treated as zeros).  out dev [R,80,Tmax]; frames >= lens[r] are written as 0. */
+int jv_estimator_forward(jv_estimator* h, int R, int Tmax, const int32_t* lens_host,
+                         const float* x, const float* mu, const float* t_host, const float* spks,
+                         const float* cond, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* CausalConditionalCFM.forward (flow_matching.py:356-401) for a ragged batch of B utterances:
+ *   x0[b] = noise[:, :len_b] * temperature      (noise dev [80, noise_stride], the seed-0 bank)
+ *   for k in 0..n-1: v = estimator(CFG pair); x += (t_span[k+1]-t_span[k]) * ((1+cfg)*v_c - cfg*v_u)
+ * mu, cond dev [B,80,Tmax] (cond may be NULL); spks dev [B,80]; t_span host [n_timesteps+1];
+ * out_mel dev [B,80,Tmax], frames >= len_b are 0.  Workspace from jv_cfm_workspace_bytes(h, 2B, lens
+ * repeated per CFG pair) — or simply jv_cfm_solve_workspace_bytes(). */
+size_t jv_cfm_solve_workspace_bytes(const jv_estimator* h, int B, const int32_t* lens_host);
+int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, const float* mu,
+                 const float* spks, const float* cond, const float* noise, int64_t noise_stride,
+                 float temperature, int n_timesteps, const float* t_span_host, float cfg_rate,
+                 float* out_mel, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HiFT vocoder = HiFTGenerator (jyutvoice/hifigan/generator.py:239-466) + ConvRNNF0Predictor
+ * (f0_predictor.py:19-55), configs/base.yaml:26-48.
+ * ------------------------------------------------------------------------------------------ */
+int jv_hift_create(int device, int precision, jv_hift** out);
+void jv_hift_destroy(jv_hift* h);
+/* `key` is the reference's HiFTGenerator state_dict key (weight-norm pairs are folded here). */
+int jv_hift_set_weight(jv_hift* h, const char* key, const float* data, const int64_t* shape, int ndim);
+int jv_hift_finalize(jv_hift* h);
+
+size_t jv_hift_workspace_bytes(const jv_hift* h, int B, const int32_t* lens_host);
+
+/* f0 = |classifier(condnet(mel))| (f0_predictor.py:52-55). mel dev [B,80,Tmax] -> f0 dev [B,Tmax]. */
+int jv_hift_f0(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* mel, float* f0,
+               void* ws, size_t ws_bytes, void* stream);
+/* Source module (generator.py:459-461,141-176,220-236): f0 dev [B,Tmax]; phase dev [B,9] (the
+ * Uniform(-pi,pi) draw, entry 0 is ignored and treated as 0); noise dev [B,9,480*Tmax] (the
+ * randn_like draw) -> s dev [B,480*Tmax].  The caller draws the RNG exactly as the reference does. */
+int jv_hift_source(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* f0,
+                   const float* phase, const float* noise, float* s, void* stream);
+/* HiFTGenerator.decode(x=mel, s) (generator.py:396-432): -> wav dev [B,480*Tmax]; samples beyond
+ * 480*len_b are 0.  Each utterance is decoded with its own zero boundary, i.e. equals the
+ * reference's unpadded batch-1 call. */
+int jv_hift_decode(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* mel,
+                   const float* s, float* wav, void* ws, size_t ws_bytes, void* stream);
+
+/* Test hook: C[M,N] = A[M,K] * W[N,K]^T (+bias) through the same GEMM engine the handles use
+ * (precision selects fp32 FFMA or bf16 tcgen05).  A, W, bias, C: dev fp32; operands are rounded to
+ * bf16 inside when precision == JV_PREC_BF16. */
+int jv_test_gemm(int precision, int M, int N, int K, const float* A, const float* W, const float* bias,
+                 float* C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JYUTVOICE_B200_H */

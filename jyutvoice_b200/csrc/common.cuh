@@ -1,0 +1,168 @@
+// Shared host/device helpers for the jyutvoice_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+#include "../../include/jyutvoice_b200.h"
+
+namespace jv {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- errors
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launch_count;
+
+#define JV_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _buf[512];                                                                              \
+      snprintf(_buf, sizeof(_buf), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      throw ::jv::Error(JV_ERR_CUDA, _buf);                                                        \
+    }                                                                                              \
+  } while (0)
+
+#define JV_REQUIRE(cond, code, ...)                                                                \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      char _buf[512];                                                                              \
+      snprintf(_buf, sizeof(_buf), __VA_ARGS__);                                                   \
+      throw ::jv::Error(code, _buf);                                                               \
+    }                                                                                              \
+  } while (0)
+
+// Count + check a kernel launch (the check is cudaPeekAtLastError: no sync).
+#define JV_LAUNCHED()                                                                              \
+  do {                                                                                             \
+    ::jv::g_launch_count.fetch_add(1, std::memory_order_relaxed);                                  \
+    JV_CUDA(cudaPeekAtLastError());                                                                \
+  } while (0)
+
+// ---------------------------------------------------------------- workspace arena (caller-owned memory)
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off;
+  bool dry;  // dry run: only measure
+  Arena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0), dry(p == nullptr) {}
+  template <typename T>
+  T* alloc(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    size_t o = off;
+    off += bytes;
+    if (dry) return nullptr;
+    JV_REQUIRE(off <= cap, JV_ERR_STATE, "workspace too small: need >= %zu bytes, have %zu", off, cap);
+    return (T*)(base + o);
+  }
+};
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return cdiv(a, b) * b; }
+
+// ---------------------------------------------------------------- dtype helpers
+template <typename T> struct DT;
+template <> struct DT<float> {
+  static constexpr int id = 0;
+  __device__ __forceinline__ static float to_f(float v) { return v; }
+  __device__ __forceinline__ static float from_f(float v) { return v; }
+};
+template <> struct DT<bf16> {
+  static constexpr int id = 1;
+  __device__ __forceinline__ static float to_f(bf16 v) { return __bfloat162float(v); }
+  __device__ __forceinline__ static bf16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// ---------------------------------------------------------------- activations (epilogue codes)
+enum Act : int {
+  ACT_NONE = 0,
+  ACT_GELU = 1,    // exact erf GELU (diffusers GELU, approximate="none")
+  ACT_ELU = 2,     // alpha = 1
+  ACT_LRELU = 3,   // slope = act_param
+  ACT_SNAKE = 4,   // x + sin^2(a x)/(a + 1e-9), a = act_vec[n]
+  ACT_MISH = 5,
+  ACT_SILU = 6,
+};
+
+__device__ __forceinline__ float act_mish(float x) {
+  // x * tanh(softplus(x)); softplus with torch's threshold 20
+  float sp = x > 20.f ? x : log1pf(expf(x));
+  return x * tanhf(sp);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float p, float a) {
+  switch (act) {
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case ACT_ELU: return v > 0.f ? v : expm1f(v);
+    case ACT_LRELU: return v > 0.f ? v : v * p;
+    case ACT_SNAKE: {
+      float s = sinf(v * a);
+      return v + (1.0f / (a + 1e-9f)) * s * s;
+    }
+    case ACT_MISH: return act_mish(v);
+    case ACT_SILU: return v / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// ---------------------------------------------------------------- GEMM-with-taps problem description
+// C[out_row(m), n] = epilogue( sum_s sum_k A_src(s)[m*a_stride + shift_s, k] * W[n, s*K_tap + k] )
+// This one form covers Linear, (causal / dilated / strided) Conv1d and the polyphase ConvTranspose1d.
+constexpr int MAX_TAPS = 16;
+
+struct GemmDesc {
+  // A operands: up to two sources (channel concat, e.g. the U-Net skip), element type = activation type
+  const void* A[2];
+  int lda[2];          // row pitch in elements
+  long a_rows[2];      // rows outside [0, a_rows) read as zero
+  int a_stride;        // a_row = m * a_stride + shift
+  int n_taps;
+  int tap_src[MAX_TAPS];
+  int tap_shift[MAX_TAPS];
+  int K_tap;           // K per tap (same for all taps)
+  const void* W;       // [N, n_taps*K_tap] K-major, activation type
+  int M, N;
+  // epilogue
+  const float* bias;   // [N] or null
+  const float* resid;  // fp32 [*, ldr] indexed by out_row, or null
+  int ldr;
+  int act;
+  float act_param;
+  const float* act_vec;
+  const int* frame_row;  // [rows] >= 0 valid, < 0 -> write 0; null = all valid (indexed by out_row)
+  float out_scale;
+  int accumulate;        // out_f32 = out_f32 + scale * v  (fp32 output only)
+  float* out_f32;        // optional fp32 output [*, ldo]
+  void* out_act;         // optional activation-typed output [*, ldo2]
+  int ldo, ldo2;
+  int act2;              // activation applied to the out_act copy only (after everything else)
+  float act2_param;
+  const float* act2_vec;
+  int o_stride, o_off;   // out_row = m * o_stride + o_off
+  long o_rows;           // out_row must be < o_rows
+};
+
+static inline GemmDesc gemm_desc_default() {
+  GemmDesc g;
+  memset(&g, 0, sizeof(g));
+  g.a_stride = 1;
+  g.out_scale = 1.f;
+  g.o_stride = 1;
+  return g;
+}
+
+}  // namespace jv

@@ -1,0 +1,572 @@
+// CausalConditionalDecoder estimator + Euler/CFG solver on B200.
+// Reference: jyutvoice/flow/decoder.py:798-1018 (estimator), jyutvoice/flow/flow_matching.py:215-265,356-401 (solver).
+#include <cmath>
+#include <memory>
+#include <algorithm>
+
+#include "engine.cuh"
+#include "kernels.cuh"
+#include "weights.cuh"
+
+namespace jv {
+
+constexpr int N_MID = 12;
+constexpr int N_TB = 4;
+constexpr int N_RESNET = 14;  // down + 12 mid + up
+constexpr int C = 256;
+
+struct LNW {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+struct ResnetW {
+  PackedW c1, c2, res;
+  LNW ln1, ln2;
+};
+struct TBlockW {
+  LNW n1, n3;
+  PackedW qkv, out, ff1, ff2;
+};
+struct GroupW {
+  ResnetW rn;
+  TBlockW tb[N_TB];
+};
+
+}  // namespace jv
+
+using namespace jv;
+
+struct jv_estimator {
+  Engine eng;
+  WeightStore store;
+  DeviceAlloc mem;
+  bool finalized = false;
+  GroupW groups[N_RESNET];  // 0 = down, 1..12 = mid, 13 = up
+  PackedW down_conv, up_conv, final_conv, final_proj;
+  LNW final_ln;
+  // time embedding (fp32, tiny): linear_1 [1024,320], linear_2 [1024,1024], 14 x mlp.1 [256,1024]
+  float *t_w1 = nullptr, *t_b1 = nullptr, *t_w2 = nullptr, *t_b2 = nullptr;
+  float* mlp_w = nullptr;  // [14*256, 1024]
+  float* mlp_b = nullptr;  // [14*256]
+};
+
+namespace jv {
+
+static PackedW make_packed(jv_estimator* h, std::vector<float>&& w, const float* bias, int N, int K_tap, int n_taps) {
+  PackedW p;
+  p.N = N;
+  p.N_pad = N;
+  p.K_tap = K_tap;
+  p.n_taps = n_taps;
+  p.W = h->mem.upload_act(w, h->eng.is_bf16());
+  p.bias = bias ? h->mem.upload_f32(pad_vec(bias, N, N)) : nullptr;
+  return p;
+}
+
+static PackedW pack_conv(jv_estimator* h, const std::string& name, int Cout, int Cin, int Kw, int n_src) {
+  const HostTensor& w = h->store.get(name + ".weight", {Cout, Cin, Kw});
+  const HostTensor& b = h->store.get(name + ".bias", {Cout});
+  const int K_tap = Cin / n_src;
+  std::vector<TapSrc> taps;
+  for (int s = 0; s < n_src; ++s)
+    for (int k = 0; k < Kw; ++k) taps.push_back({k, s * K_tap, K_tap});
+  return make_packed(h, pack_conv_taps(w.data.data(), Cout, Cin, Kw, taps, K_tap, Cout), b.data.data(), Cout, K_tap, (int)taps.size());
+}
+
+static PackedW pack_linear(jv_estimator* h, const std::string& name, int N, int K, bool bias) {
+  const HostTensor& w = h->store.get(name + ".weight", {N, K});
+  const float* b = bias ? h->store.get(name + ".bias", {N}).data.data() : nullptr;
+  std::vector<float> v(w.data);
+  return make_packed(h, std::move(v), b, N, K, 1);
+}
+
+static LNW pack_ln(jv_estimator* h, const std::string& name) {
+  LNW l;
+  l.g = h->mem.upload_f32(h->store.get(name + ".weight", {C}).data);
+  l.b = h->mem.upload_f32(h->store.get(name + ".bias", {C}).data);
+  return l;
+}
+
+static void finalize_impl(jv_estimator* h) {
+  JV_REQUIRE(!h->finalized, JV_ERR_STATE, "estimator already finalised");
+  JV_CUDA(cudaSetDevice(h->eng.device));
+  auto group_names = [](int g, std::string& rn, std::string& tb) {
+    if (g == 0) { rn = "down_blocks.0.0"; tb = "down_blocks.0.1"; }
+    else if (g == N_RESNET - 1) { rn = "up_blocks.0.0"; tb = "up_blocks.0.1"; }
+    else { rn = "mid_blocks." + std::to_string(g - 1) + ".0"; tb = "mid_blocks." + std::to_string(g - 1) + ".1"; }
+  };
+  std::vector<float> mlp_w((size_t)N_RESNET * C * 1024), mlp_b((size_t)N_RESNET * C);
+  for (int g = 0; g < N_RESNET; ++g) {
+    std::string rn, tb;
+    group_names(g, rn, tb);
+    const int cin = g == 0 ? 320 : (g == N_RESNET - 1 ? 512 : 256);
+    const int n_src = g == N_RESNET - 1 ? 2 : 1;
+    GroupW& G = h->groups[g];
+    G.rn.c1 = pack_conv(h, rn + ".block1.block.0", C, cin, 3, n_src);
+    G.rn.ln1 = pack_ln(h, rn + ".block1.block.2");
+    G.rn.c2 = pack_conv(h, rn + ".block2.block.0", C, C, 3, 1);
+    G.rn.ln2 = pack_ln(h, rn + ".block2.block.2");
+    G.rn.res = pack_conv(h, rn + ".res_conv", C, cin, 1, n_src);
+    const HostTensor& mw = h->store.get(rn + ".mlp.1.weight", {C, 1024});
+    const HostTensor& mb = h->store.get(rn + ".mlp.1.bias", {C});
+    std::copy(mw.data.begin(), mw.data.end(), mlp_w.begin() + (size_t)g * C * 1024);
+    std::copy(mb.data.begin(), mb.data.end(), mlp_b.begin() + (size_t)g * C);
+    for (int j = 0; j < N_TB; ++j) {
+      const std::string p = tb + "." + std::to_string(j);
+      TBlockW& T = G.tb[j];
+      T.n1 = pack_ln(h, p + ".norm1");
+      T.n3 = pack_ln(h, p + ".norm3");
+      const HostTensor& wq = h->store.get(p + ".attn1.to_q.weight", {512, C});
+      const HostTensor& wk = h->store.get(p + ".attn1.to_k.weight", {512, C});
+      const HostTensor& wv = h->store.get(p + ".attn1.to_v.weight", {512, C});
+      std::vector<float> qkv;
+      qkv.reserve(3 * 512 * C);
+      qkv.insert(qkv.end(), wq.data.begin(), wq.data.end());
+      qkv.insert(qkv.end(), wk.data.begin(), wk.data.end());
+      qkv.insert(qkv.end(), wv.data.begin(), wv.data.end());
+      T.qkv = make_packed(h, std::move(qkv), nullptr, 1536, C, 1);
+      T.out = pack_linear(h, p + ".attn1.to_out.0", C, 512, true);
+      T.ff1 = pack_linear(h, p + ".ff.net.0.proj", 1024, C, true);
+      T.ff2 = pack_linear(h, p + ".ff.net.2", C, 1024, true);
+    }
+  }
+  h->down_conv = pack_conv(h, "down_blocks.0.2", C, C, 3, 1);
+  h->up_conv = pack_conv(h, "up_blocks.0.2", C, C, 3, 1);
+  h->final_conv = pack_conv(h, "final_block.block.0", C, C, 3, 1);
+  h->final_ln = pack_ln(h, "final_block.block.2");
+  h->final_proj = pack_conv(h, "final_proj", 80, C, 1, 1);
+  h->t_w1 = h->mem.upload_f32(h->store.get("time_mlp.linear_1.weight", {1024, 320}).data);
+  h->t_b1 = h->mem.upload_f32(h->store.get("time_mlp.linear_1.bias", {1024}).data);
+  h->t_w2 = h->mem.upload_f32(h->store.get("time_mlp.linear_2.weight", {1024, 1024}).data);
+  h->t_b2 = h->mem.upload_f32(h->store.get("time_mlp.linear_2.bias", {1024}).data);
+  h->mlp_w = h->mem.upload_f32(mlp_w);
+  h->mlp_b = h->mem.upload_f32(mlp_b);
+  JV_REQUIRE(h->store.t.size() == 910, JV_ERR_STATE, "expected 910 estimator tensors, got %zu (unexpected keys present)",
+             h->store.t.size());
+  h->store.t.clear();
+  JV_CUDA(cudaDeviceSynchronize());
+  h->finalized = true;
+}
+
+// ------------------------------------------------------------------------------------------ workspace
+struct EstLayout {
+  int R = 0, M = 0, M_alloc = 0;
+  std::vector<int> row_off, row_len, frame_row;
+};
+
+static EstLayout make_layout(int R, const int32_t* lens) {
+  EstLayout L;
+  L.R = R;
+  L.row_off.resize(R + 1);
+  L.row_len.assign(lens, lens + R);
+  int off = 0;
+  for (int r = 0; r < R; ++r) {
+    JV_REQUIRE(lens[r] >= 1, JV_ERR_INVALID, "lens[%d] = %d must be >= 1", r, lens[r]);
+    L.row_off[r] = off;
+    off += lens[r] + EST_GAP;
+  }
+  L.row_off[R] = off;
+  L.M = off;
+  L.M_alloc = round_up(off, 128);
+  L.frame_row.assign(L.M_alloc, -1);
+  for (int r = 0; r < R; ++r)
+    for (int t = 0; t < lens[r]; ++t) L.frame_row[L.row_off[r] + t] = r;
+  return L;
+}
+
+struct EstBuffers {
+  int *frame_row, *row_off, *row_len, *row_tidx;
+  float* temb;   // [nt, 14, 256]
+  float* tsin;   // [nt, 320]
+  float* th1;    // [nt, 1024]
+  float* th2;    // [nt, 1024]
+  void *A0, *XA, *XB, *SKIP, *H, *QKV, *ATT, *FF;
+  float *X, *Y, *RES, *V;
+};
+
+static EstBuffers carve(Arena& ar, const Engine& eng, int M_alloc, int R, int nt) {
+  EstBuffers b;
+  const size_t es = eng.act_size();
+  b.frame_row = ar.alloc<int>(M_alloc);
+  b.row_off = ar.alloc<int>(R + 1);
+  b.row_len = ar.alloc<int>(R);
+  b.row_tidx = ar.alloc<int>(R);
+  b.temb = ar.alloc<float>((size_t)nt * N_RESNET * C);
+  b.tsin = ar.alloc<float>((size_t)nt * 320);
+  b.th1 = ar.alloc<float>((size_t)nt * 1024);
+  b.th2 = ar.alloc<float>((size_t)nt * 1024);
+  b.A0 = ar.alloc<char>((size_t)M_alloc * 320 * es);
+  b.XA = ar.alloc<char>((size_t)M_alloc * C * es);
+  b.XB = ar.alloc<char>((size_t)M_alloc * C * es);
+  b.SKIP = ar.alloc<char>((size_t)M_alloc * C * es);
+  b.H = ar.alloc<char>((size_t)M_alloc * C * es);
+  b.QKV = ar.alloc<char>((size_t)M_alloc * 1536 * es);
+  b.ATT = ar.alloc<char>((size_t)M_alloc * 512 * es);
+  b.FF = ar.alloc<char>((size_t)M_alloc * 1024 * es);
+  b.X = ar.alloc<float>((size_t)M_alloc * C);
+  b.Y = ar.alloc<float>((size_t)M_alloc * C);
+  b.RES = ar.alloc<float>((size_t)M_alloc * C);
+  b.V = ar.alloc<float>((size_t)M_alloc * 80);
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+struct FwdCtx {
+  jv_estimator* h;
+  EstBuffers b;
+  int M, M_alloc, R, Tmax_len;  // Tmax_len: longest row (attention grid)
+  const float* temb_step;       // temb rows of the current step: [*, 14, 256]
+  cudaStream_t st;
+};
+
+static GemmDesc conv_desc(const FwdCtx& c, const PackedW& w, const void* A0p, const void* A1p, int Kw) {
+  GemmDesc g = gemm_desc_default();
+  g.A[0] = A0p;
+  g.A[1] = A1p;
+  g.lda[0] = g.lda[1] = w.K_tap;
+  g.a_rows[0] = g.a_rows[1] = c.M_alloc;
+  g.n_taps = w.n_taps;
+  g.K_tap = w.K_tap;
+  const int n_src = A1p ? 2 : 1;
+  for (int s = 0; s < n_src; ++s)
+    for (int k = 0; k < Kw; ++k) {
+      g.tap_src[s * Kw + k] = s;
+      g.tap_shift[s * Kw + k] = k - (Kw - 1);  // causal: taps read t-2, t-1, t
+    }
+  g.W = w.W;
+  g.M = c.M_alloc;
+  g.N = w.N;
+  g.bias = w.bias;
+  g.frame_row = c.b.frame_row;
+  g.o_rows = c.M_alloc;
+  return g;
+}
+
+static void run_ln(const FwdCtx& c, const float* x, const LNW& ln, bool mish, const float* add_row, const float* add_mat,
+                   float* out_f32, void* out_act) {
+  LnArgs a;
+  a.x = x; a.ldx = C;
+  a.gamma = ln.g; a.beta = ln.b;
+  a.mish = mish ? 1 : 0;
+  a.add_row = add_row; a.row_tidx = c.b.row_tidx; a.add_row_stride = N_RESNET * C;
+  a.add_mat = add_mat; a.ld_add = C;
+  a.frame_row = c.b.frame_row;
+  a.out_f32 = out_f32; a.ldo = C;
+  a.out_act = out_act; a.ldo2 = C;
+  a.M = c.M_alloc;
+  const int blocks = cdiv(c.M_alloc * 32, 256);
+  if (c.h->eng.is_bf16()) ln256_kernel<bf16><<<blocks, 256, 0, c.st>>>(a);
+  else ln256_kernel<float><<<blocks, 256, 0, c.st>>>(a);
+  JV_LAUNCHED();
+}
+
+static void run_attention(const FwdCtx& c) {
+  static bool attr = false;
+  if (!attr) {
+    JV_CUDA(cudaFuncSetAttribute(attention_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    JV_CUDA(cudaFuncSetAttribute(attention_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    attr = true;
+  }
+  dim3 grid(cdiv(c.Tmax_len, 64), 8, c.R);
+  if (c.h->eng.is_bf16())
+    attention_simt_kernel<bf16><<<grid, 256, ATT_SMEM_BYTES, c.st>>>((const bf16*)c.b.QKV, 1536, (bf16*)c.b.ATT, 512, c.b.row_off,
+                                                                     c.b.row_len, 0.125f);
+  else
+    attention_simt_kernel<float><<<grid, 256, ATT_SMEM_BYTES, c.st>>>((const float*)c.b.QKV, 1536, (float*)c.b.ATT, 512,
+                                                                      c.b.row_off, c.b.row_len, 0.125f);
+  JV_LAUNCHED();
+}
+
+// resnet (decoder.py:110-115) over conv input(s) in0 (+ in1 for the skip concat); result -> X (fp32 stream)
+static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void* in0, const void* in1) {
+  Engine& e = c.h->eng;
+  GemmDesc g = conv_desc(c, w.c1, in0, in1, 3);
+  g.out_f32 = c.b.Y; g.ldo = C;
+  e.gemm(g, c.st);
+  g = conv_desc(c, w.res, in0, in1, 1);
+  g.out_f32 = c.b.RES; g.ldo = C;
+  e.gemm(g, c.st);
+  // h = (Mish(LN(conv1)) + mlp(t)) * mask  -> H (conv2 input)
+  run_ln(c, c.b.Y, w.ln1, true, c.temb_step + (size_t)layer * C, nullptr, nullptr, c.b.H);
+  g = conv_desc(c, w.c2, c.b.H, nullptr, 3);
+  g.out_f32 = c.b.Y; g.ldo = C;
+  e.gemm(g, c.st);
+  // x = Mish(LN(conv2)) * mask + res_conv(x * mask)
+  run_ln(c, c.b.Y, w.ln2, true, nullptr, c.b.RES, c.b.X, nullptr);
+}
+
+// BasicTransformerBlock (transformer.py:355-443); `copy_to`: activation-typed copy of the block output (conv input)
+static void run_tblock(const FwdCtx& c, const TBlockW& w, void* copy_to) {
+  Engine& e = c.h->eng;
+  run_ln(c, c.b.X, w.n1, false, nullptr, nullptr, nullptr, c.b.H);
+  GemmDesc g = conv_desc(c, w.qkv, c.b.H, nullptr, 1);
+  g.out_act = c.b.QKV; g.ldo2 = 1536;
+  e.gemm(g, c.st);
+  run_attention(c);
+  g = conv_desc(c, w.out, c.b.ATT, nullptr, 1);
+  g.resid = c.b.X; g.ldr = C;
+  g.out_f32 = c.b.X; g.ldo = C;
+  e.gemm(g, c.st);
+  run_ln(c, c.b.X, w.n3, false, nullptr, nullptr, nullptr, c.b.H);
+  g = conv_desc(c, w.ff1, c.b.H, nullptr, 1);
+  g.act = ACT_GELU;
+  g.out_act = c.b.FF; g.ldo2 = 1024;
+  e.gemm(g, c.st);
+  g = conv_desc(c, w.ff2, c.b.FF, nullptr, 1);
+  g.resid = c.b.X; g.ldr = C;
+  g.out_f32 = c.b.X; g.ldo = C;
+  if (copy_to) { g.out_act = copy_to; g.ldo2 = C; }
+  e.gemm(g, c.st);
+}
+
+// A0 (packed [M,320]) -> V (fp32 [M,80], masked)
+static void forward_packed(const FwdCtx& c) {
+  jv_estimator* h = c.h;
+  Engine& e = h->eng;
+  for (int gi = 0; gi < N_RESNET; ++gi) {
+    const GroupW& G = h->groups[gi];
+    const void* in0 = gi == 0 ? c.b.A0 : (gi == N_RESNET - 1 ? c.b.XA : c.b.XA);
+    const void* in1 = gi == N_RESNET - 1 ? c.b.SKIP : nullptr;
+    if (gi == 1) in0 = c.b.XB;  // output of the down CausalConv1d
+    run_resnet(c, G.rn, gi, in0, in1);
+    for (int j = 0; j < N_TB; ++j) {
+      void* copy_to = nullptr;
+      if (j == N_TB - 1) copy_to = gi == 0 ? c.b.SKIP : c.b.XA;
+      run_tblock(c, G.tb[j], copy_to);
+    }
+    if (gi == 0) {  // x = CausalConv1d(x * mask) (decoder.py:968)
+      GemmDesc g = conv_desc(c, h->down_conv, c.b.SKIP, nullptr, 3);
+      g.out_act = c.b.XB; g.ldo2 = C;
+      e.gemm(g, c.st);
+    }
+  }
+  GemmDesc g = conv_desc(c, h->up_conv, c.b.XA, nullptr, 3);  // decoder.py:1015
+  g.out_act = c.b.XB; g.ldo2 = C;
+  e.gemm(g, c.st);
+  g = conv_desc(c, h->final_conv, c.b.XB, nullptr, 3);  // final_block
+  g.out_f32 = c.b.Y; g.ldo = C;
+  e.gemm(g, c.st);
+  run_ln(c, c.b.Y, h->final_ln, true, nullptr, nullptr, nullptr, c.b.H);
+  g = conv_desc(c, h->final_proj, c.b.H, nullptr, 1);
+  g.out_f32 = c.b.V; g.ldo = 80;
+  e.gemm(g, c.st);
+}
+
+// sinusoidal embedding (decoder.py:21-30) on the host in double, rounded to fp32
+static void host_sinusoid(const float* t, int nt, std::vector<float>& out) {
+  out.resize((size_t)nt * 320);
+  const float neg = (float)(-(std::log(10000.0) / 159.0));
+  for (int i = 0; i < nt; ++i) {
+    const float ts = 1000.0f * t[i];
+    for (int k = 0; k < 160; ++k) {
+      const float f = (float)std::exp((double)((float)k * neg));
+      const float e = ts * f;
+      out[(size_t)i * 320 + k] = (float)std::sin((double)e);
+      out[(size_t)i * 320 + 160 + k] = (float)std::cos((double)e);
+    }
+  }
+}
+
+// temb[i, layer, :] = mlp_layer(Mish(time_mlp(sinusoid(t_i))))
+static void run_time_embedding(const FwdCtx& c, const float* t_host, int nt) {
+  jv_estimator* h = c.h;
+  std::vector<float> e;
+  host_sinusoid(t_host, nt, e);
+  JV_CUDA(cudaMemcpyAsync(c.b.tsin, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, c.st));
+  JV_CUDA(cudaStreamSynchronize(c.st));  // `e` is a stack-owned staging buffer
+  gemv_rows_kernel<<<cdiv(nt * 1024 * 32, 256), 256, 0, c.st>>>(h->t_w1, h->t_b1, c.b.tsin, c.b.th1, nt, 1024, 320, ACT_NONE, ACT_SILU, 1024);
+  JV_LAUNCHED();
+  gemv_rows_kernel<<<cdiv(nt * 1024 * 32, 256), 256, 0, c.st>>>(h->t_w2, h->t_b2, c.b.th1, c.b.th2, nt, 1024, 1024, ACT_NONE, ACT_NONE, 1024);
+  JV_LAUNCHED();
+  gemv_rows_kernel<<<cdiv(nt * N_RESNET * C * 32, 256), 256, 0, c.st>>>(h->mlp_w, h->mlp_b, c.b.th2, c.b.temb, nt, N_RESNET * C, 1024,
+                                                                        ACT_MISH, ACT_NONE, N_RESNET * C);
+  JV_LAUNCHED();
+}
+
+static void upload_layout(const FwdCtx& c, const EstLayout& L, const std::vector<int>& tidx) {
+  JV_CUDA(cudaMemcpyAsync(c.b.frame_row, L.frame_row.data(), L.frame_row.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  JV_CUDA(cudaMemcpyAsync(c.b.row_off, L.row_off.data(), L.row_off.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  JV_CUDA(cudaMemcpyAsync(c.b.row_len, L.row_len.data(), L.row_len.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  JV_CUDA(cudaMemcpyAsync(c.b.row_tidx, tidx.data(), tidx.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  JV_CUDA(cudaStreamSynchronize(c.st));  // host vectors die with the caller's frame
+}
+
+template <typename TA>
+static void launch_pack(const FwdCtx& c, const float* x, const float* mu, const float* spks, const float* cond, int Tmax, int cfg) {
+  const long n = (long)c.M_alloc * 320;
+  pack_input_kernel<TA><<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>((TA*)c.b.A0, c.b.frame_row, c.b.row_off, c.M_alloc, x, mu, spks,
+                                                                       cond, Tmax, cfg);
+  JV_LAUNCHED();
+}
+
+static void run_pack(const FwdCtx& c, const float* x, const float* mu, const float* spks, const float* cond, int Tmax, int cfg) {
+  if (c.h->eng.is_bf16()) launch_pack<bf16>(c, x, mu, spks, cond, Tmax, cfg);
+  else launch_pack<float>(c, x, mu, spks, cond, Tmax, cfg);
+}
+
+static size_t workspace_bytes(const jv_estimator* h, int R, const int32_t* lens, int nt) {
+  EstLayout L = make_layout(R, lens);
+  Arena ar(nullptr, 0);
+  carve(ar, h->eng, L.M_alloc, R, nt);
+  ar.alloc<int>(R);  // lens copy (solver)
+  return ar.off + 256;
+}
+
+}  // namespace jv
+
+// =========================================================================================== C ABI
+#define JV_API_BEGIN try {
+#define JV_API_END                                   \
+  }                                                  \
+  catch (const jv::Error& e) {                       \
+    jv::set_last_error(e.what());                    \
+    return e.code;                                   \
+  }                                                  \
+  catch (const std::exception& e) {                  \
+    jv::set_last_error(e.what());                    \
+    return JV_ERR_CUDA;                              \
+  }                                                  \
+  return JV_OK;
+
+extern "C" {
+
+int jv_estimator_create(int device, int precision, jv_estimator** out) {
+  JV_API_BEGIN
+  JV_REQUIRE(out != nullptr, JV_ERR_INVALID, "out is NULL");
+  std::unique_ptr<jv_estimator> h(new jv_estimator());
+  h->eng.init(device, precision);
+  *out = h.release();
+  JV_API_END
+}
+
+void jv_estimator_destroy(jv_estimator* h) { delete h; }
+
+int jv_estimator_set_weight(jv_estimator* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+  JV_API_BEGIN
+  JV_REQUIRE(h != nullptr, JV_ERR_INVALID, "handle is NULL");
+  JV_REQUIRE(!h->finalized, JV_ERR_STATE, "estimator already finalised");
+  JV_CUDA(cudaSetDevice(h->eng.device));
+  h->store.set(key, data, shape, ndim);
+  JV_API_END
+}
+
+int jv_estimator_finalize(jv_estimator* h) {
+  JV_API_BEGIN
+  JV_REQUIRE(h != nullptr, JV_ERR_INVALID, "handle is NULL");
+  finalize_impl(h);
+  JV_API_END
+}
+
+size_t jv_cfm_workspace_bytes(const jv_estimator* h, int n_rows, const int32_t* lens_host) {
+  try {
+    if (!h || n_rows < 1 || !lens_host) return 0;
+    return workspace_bytes(h, n_rows, lens_host, n_rows);
+  } catch (const std::exception& e) {
+    jv::set_last_error(e.what());
+    return 0;
+  }
+}
+
+size_t jv_cfm_solve_workspace_bytes(const jv_estimator* h, int B, const int32_t* lens_host) {
+  try {
+    if (!h || B < 1 || !lens_host) return 0;
+    std::vector<int32_t> l2(2 * (size_t)B);
+    for (int b = 0; b < B; ++b) l2[2 * b] = l2[2 * b + 1] = lens_host[b];
+    return workspace_bytes(h, 2 * B, l2.data(), 64);
+  } catch (const std::exception& e) {
+    jv::set_last_error(e.what());
+    return 0;
+  }
+}
+
+int jv_estimator_forward(jv_estimator* h, int R, int Tmax, const int32_t* lens_host, const float* x, const float* mu,
+                         const float* t_host, const float* spks, const float* cond, float* out, void* ws, size_t ws_bytes,
+                         void* stream) {
+  JV_API_BEGIN
+  JV_REQUIRE(h && h->finalized, JV_ERR_STATE, "estimator not finalised");
+  JV_REQUIRE(R >= 1 && Tmax >= 1 && lens_host && x && mu && t_host && out && ws, JV_ERR_INVALID, "bad arguments");
+  JV_CUDA(cudaSetDevice(h->eng.device));
+  EstLayout L = make_layout(R, lens_host);
+  int tmax_len = 0;
+  for (int r = 0; r < R; ++r) {
+    JV_REQUIRE(lens_host[r] <= Tmax, JV_ERR_INVALID, "lens[%d] = %d exceeds Tmax = %d", r, lens_host[r], Tmax);
+    tmax_len = std::max(tmax_len, lens_host[r]);
+  }
+  Arena ar(ws, ws_bytes);
+  FwdCtx c;
+  c.h = h;
+  c.b = carve(ar, h->eng, L.M_alloc, R, R);
+  int* lens_dev = ar.alloc<int>(R);
+  c.M = L.M; c.M_alloc = L.M_alloc; c.R = R; c.Tmax_len = tmax_len;
+  c.st = (cudaStream_t)stream;
+  c.temb_step = c.b.temb;
+  std::vector<int> tidx(R);
+  for (int r = 0; r < R; ++r) tidx[r] = r;
+  JV_CUDA(cudaMemcpyAsync(lens_dev, lens_host, R * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  upload_layout(c, L, tidx);
+  run_time_embedding(c, t_host, R);
+  run_pack(c, x, mu, spks, cond, Tmax, 0);
+  forward_packed(c);
+  const long n = (long)R * 80 * Tmax;
+  unpack_output_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(out, c.b.V, 80, c.b.row_off, lens_dev, R, Tmax);
+  JV_LAUNCHED();
+  JV_API_END
+}
+
+int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, const float* mu, const float* spks,
+                 const float* cond, const float* noise, int64_t noise_stride, float temperature, int n_timesteps,
+                 const float* t_span_host, float cfg_rate, float* out_mel, void* ws, size_t ws_bytes, void* stream) {
+  JV_API_BEGIN
+  JV_REQUIRE(h && h->finalized, JV_ERR_STATE, "estimator not finalised");
+  JV_REQUIRE(B >= 1 && Tmax >= 1 && lens_host && mu && spks && noise && t_span_host && out_mel && ws, JV_ERR_INVALID, "bad arguments");
+  JV_REQUIRE(n_timesteps >= 1 && n_timesteps <= 64, JV_ERR_INVALID, "n_timesteps = %d out of range [1, 64]", n_timesteps);
+  JV_CUDA(cudaSetDevice(h->eng.device));
+  const int R = 2 * B;
+  std::vector<int32_t> l2(R);
+  int tmax_len = 0;
+  for (int b = 0; b < B; ++b) {
+    JV_REQUIRE(lens_host[b] >= 1 && lens_host[b] <= Tmax, JV_ERR_INVALID, "lens[%d] = %d outside [1, Tmax = %d]", b, lens_host[b], Tmax);
+    JV_REQUIRE(lens_host[b] <= noise_stride, JV_ERR_INVALID, "lens[%d] = %d exceeds the noise bank (%lld frames)", b, lens_host[b],
+               (long long)noise_stride);
+    l2[2 * b] = l2[2 * b + 1] = lens_host[b];
+    tmax_len = std::max(tmax_len, lens_host[b]);
+  }
+  EstLayout L = make_layout(R, l2.data());
+  Arena ar(ws, ws_bytes);
+  FwdCtx c;
+  c.h = h;
+  c.b = carve(ar, h->eng, L.M_alloc, R, 64);
+  int* lens_dev = ar.alloc<int>(R);
+  c.M = L.M; c.M_alloc = L.M_alloc; c.R = R; c.Tmax_len = tmax_len;
+  c.st = (cudaStream_t)stream;
+  c.temb_step = c.b.temb;
+  std::vector<int> tidx(R, 0);
+  JV_CUDA(cudaMemcpyAsync(lens_dev, lens_host, B * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  upload_layout(c, L, tidx);
+  // Euler bookkeeping exactly as flow_matching.py:230-263 (t and dt accumulate in fp32)
+  std::vector<float> ts(n_timesteps), dts(n_timesteps);
+  {
+    float t = t_span_host[0];
+    float dt = t_span_host[1] - t_span_host[0];
+    for (int k = 1; k <= n_timesteps; ++k) {
+      ts[k - 1] = t;
+      dts[k - 1] = dt;
+      t = t + dt;
+      if (k < n_timesteps) dt = t_span_host[k + 1] - t;
+    }
+  }
+  run_time_embedding(c, ts.data(), n_timesteps);  // all steps at once: temb depends on t only
+  const long nx = (long)B * 80 * Tmax;
+  init_noise_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, c.st>>>(out_mel, noise, noise_stride, lens_dev, B, Tmax, temperature);
+  JV_LAUNCHED();
+  for (int k = 0; k < n_timesteps; ++k) {
+    c.temb_step = c.b.temb + (size_t)k * N_RESNET * C;  // every row of step k shares t_k (row_tidx == 0)
+    run_pack(c, out_mel, mu, spks, cond, Tmax, 1);
+    forward_packed(c);
+    cfg_euler_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, c.st>>>(out_mel, c.b.V, 80, c.b.row_off, lens_dev, B, Tmax, dts[k], cfg_rate);
+    JV_LAUNCHED();
+  }
+  JV_API_END
+}
+
+}  // extern "C"

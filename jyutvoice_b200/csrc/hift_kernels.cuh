@@ -1,0 +1,240 @@
+// Non-GEMM kernels of the HiFT vocoder: mel packing, f0 head, NSF source, STFT, Snake / leaky-ReLU
+// rows, reflection fix-up, conv_post head + inverse STFT.
+#pragma once
+#include "common.cuh"
+
+namespace jv {
+
+// Packed layout: utterance b owns mel frames [off_b, off_b + T_b) followed by HIFT_GAP zero frames;
+// a stage with rate r (1, 8, 40, 120) keeps frame (r*off_b + p).  The zero gap is >= the largest
+// conv reach at every stage (k=11, dilation 5 -> 25 rows <= 8*4), so every utterance sees the zero
+// padding of the reference's unpadded batch-1 call.
+constexpr int HIFT_GAP = 4;
+
+struct HiftSeq {
+  const int* off;  // [B+1] mel-frame offsets
+  const int* len;  // [B] mel frames
+  int B;
+};
+
+// frame_row for a stage: rows [rate*off_b, rate*off_b + rate*len_b + extra) -> b, else -1
+__global__ void hift_frame_row_kernel(int* __restrict__ fr, int rows, HiftSeq sq, int rate, int extra) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  int v = -1;
+  for (int b = 0; b < sq.B; ++b) {
+    int s = rate * sq.off[b];
+    if (m >= s && m < s + rate * sq.len[b] + extra) { v = b; break; }
+  }
+  fr[m] = v;
+}
+
+// MEL[m, 0:128] = mel[b, c, t] (c < 80), zero elsewhere
+template <typename TA>
+__global__ void hift_pack_mel_kernel(TA* __restrict__ MEL, const int* __restrict__ fr, HiftSeq sq, int rows,
+                                     const float* __restrict__ mel, int Tmax) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)rows * 128) return;
+  int m = (int)(idx >> 7), c = (int)(idx & 127);
+  int b = fr[m];
+  float v = 0.f;
+  if (b >= 0 && c < 80) v = mel[((long)b * 80 + c) * Tmax + (m - sq.off[b])];
+  MEL[idx] = DT<TA>::from_f(v);
+}
+
+// f0[b, t] = | w . h[m, :512] + bias |   (f0_predictor.py:52-55), one warp per frame
+template <typename TA>
+__global__ void __launch_bounds__(256) hift_f0_head_kernel(const TA* __restrict__ Hh, const int* __restrict__ fr, HiftSeq sq, int rows,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           float* __restrict__ f0, int Tmax) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int b = fr[warp];
+  if (b < 0) return;
+  float s = 0.f;
+  for (int k = lane; k < 512; k += 32) s = fmaf(DT<TA>::to_f(Hh[(long)warp * 512 + k]), __ldg(w + k), s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) f0[(long)b * Tmax + (warp - sq.off[b])] = fabsf(s + bias[0]);
+}
+
+__global__ void zero_f32_kernel(float* __restrict__ p, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+// ---------------------------------------------------------------- NSF source (generator.py:141-176, 220-236)
+// Phase prefix per (b, harmonic): D[b,h,t] = sum_{t'<t} 480 * F[b,h,t'] accumulated in fp64 — torch's CPU
+// cumsum accumulates fp32 inputs in double and rounds each output to float (ATen cumsum_cpu_kernel, acc_type).
+__global__ void hift_phase_prefix_kernel(const float* __restrict__ f0, int Tmax, const int* __restrict__ len, int B,
+                                         double* __restrict__ D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 9) return;
+  int b = i / 9, h = i % 9;
+  double acc = 0.0;
+  const int T = len[b];
+  for (int t = 0; t < T; ++t) {
+    D[((long)b * 9 + h) * Tmax + t] = acc;
+    float F = f0[(long)b * Tmax + t] * (float)(h + 1) / 24000.0f;
+    acc += 480.0 * (double)F;
+  }
+}
+
+__global__ void hift_source_kernel(const float* __restrict__ f0, const double* __restrict__ D, const float* __restrict__ phase,
+                                   const float* __restrict__ noise, const float* __restrict__ lw, const float* __restrict__ lb,
+                                   const int* __restrict__ len, int B, int Tmax, float* __restrict__ s) {
+  const long L = 480L * Tmax;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * L) return;
+  const int b = (int)(idx / L);
+  const long j = idx % L;
+  const int t = (int)(j / 480), jj = (int)(j % 480);
+  if (t >= len[b]) { s[idx] = 0.f; return; }
+  const float f = f0[(long)b * Tmax + t];
+  const float uv = f > 10.0f ? 1.0f : 0.0f;
+  const float noise_amp = f > 10.0f ? 0.003f : (0.1f / 3.0f);
+  float acc = lb[0];
+#pragma unroll
+  for (int h = 0; h < 9; ++h) {
+    const float F = f * (float)(h + 1) / 24000.0f;
+    const double cum = D[((long)b * 9 + h) * Tmax + t] + (double)(jj + 1) * (double)F;
+    const float cf = (float)cum;
+    const float frac = cf - floorf(cf);  // fp32 `% 1` of a non-negative value
+    const float theta = 6.283185307179586f * frac;
+    const float ph = h == 0 ? 0.f : phase[b * 9 + h];
+    const float sine = 0.1f * sinf(theta + ph);
+    const float v = sine * uv + noise_amp * noise[((long)b * 9 + h) * L + j];
+    acc = fmaf(lw[h], v, acc);
+  }
+  s[idx] = tanhf(acc);
+}
+
+// ---------------------------------------------------------------- STFT of the source (generator.py:371-381)
+// 16-point DFT, hop 4, periodic hann, center + reflect padding (per utterance at its own length).
+struct StftTables {
+  float wc[9][16];  // w[n] * cos(2 pi k n / 16)
+  float ws[9][16];  // -w[n] * sin(2 pi k n / 16)
+};
+
+template <typename TA>
+__global__ void hift_stft_kernel(TA* __restrict__ SST, const int* __restrict__ fr, HiftSeq sq, int rows,
+                                 const float* __restrict__ s, int Tmax, const StftTables tb) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  const int b = fr[m];
+  TA* o = SST + (long)m * 18;
+  if (b < 0) {
+#pragma unroll
+    for (int k = 0; k < 18; ++k) o[k] = DT<TA>::from_f(0.f);
+    return;
+  }
+  const int f = m - 120 * sq.off[b];
+  const int L = 480 * sq.len[b];
+  const float* sb = s + (long)b * 480 * Tmax;
+  float x[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    int i = 4 * f - 8 + n;
+    if (i < 0) i = -i;
+    if (i >= L) i = 2 * (L - 1) - i;
+    x[n] = sb[i];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      re = fmaf(x[n], tb.wc[k][n], re);
+      im = fmaf(x[n], tb.ws[k][n], im);
+    }
+    o[k] = DT<TA>::from_f(re);
+    o[9 + k] = DT<TA>::from_f(im);
+  }
+}
+
+// ---------------------------------------------------------------- elementwise rows: out = act(in) (fp32 in, TA out)
+template <typename TA>
+__global__ void act_rows_kernel(const float* __restrict__ in, TA* __restrict__ out, long n, int Cn, int act, float p,
+                                const float* __restrict__ vec) {
+  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float4 v = *reinterpret_cast<const float4*>(in + i);
+  const int c = (int)(i % Cn);
+  float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r[j] = apply_act(r[j], act, p, vec ? __ldg(vec + c + j) : 0.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[i + j] = DT<TA>::from_f(r[j]);
+}
+
+// ReflectionPad1d((1,0)) at stage 2 (generator.py:407-408): position 0 := position 2 (= u[1])
+__global__ void hift_reflect_fix_kernel(float* __restrict__ X, int Cn, HiftSeq sq, int rate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sq.B * Cn) return;
+  int b = i / Cn, c = i % Cn;
+  long r0 = (long)rate * sq.off[b];
+  X[r0 * Cn + c] = X[(r0 + 2) * Cn + c];
+}
+
+// ---------------------------------------------------------------- output head (generator.py:425-431, 383-394)
+// SPEC[m, 0:9] = log-magnitude, SPEC[m, 9:18] = pre-sin phase for frame m.  y[n] = OLA / envelope, clamp.
+struct IstftTables {
+  float cr[9][16];  // c_k cos(2 pi k j / 16) / 16 * w[j]
+  float ci[9][16];  // -c_k sin(2 pi k j / 16) / 16 * w[j]  (0 for k = 0, 8)
+  float w2[16];
+};
+
+__global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict__ SPEC, int ld, HiftSeq sq, int Tmax,
+                                                         float* __restrict__ wav, const IstftTables tb, float limit) {
+  __shared__ float re[67][9];
+  __shared__ float im[67][9];
+  const int b = blockIdx.y;
+  const int T = sq.len[b];
+  const int n0 = blockIdx.x * 256;  // first output sample of this block
+  const long Lmax = 480L * Tmax;
+  if (n0 >= 480 * Tmax) return;
+  const int F = 120 * T + 1;
+  const int f_lo = n0 / 4 + 2 - 3;  // frames f_lo .. f_lo + 66 cover samples n0 .. n0 + 255
+  const long row0 = 120L * sq.off[b];
+  for (int i = threadIdx.x; i < 67 * 9; i += 256) {
+    const int fi = i / 9, k = i % 9;
+    const int f = f_lo + fi;
+    float r = 0.f, q = 0.f;
+    if (f >= 0 && f < F) {
+      const float* sp = SPEC + (row0 + f) * ld;
+      const float mag = fminf(expf(sp[k]), 100.0f);
+      const float ph = sinf(sp[9 + k]);
+      float sn, cs;
+      sincosf(ph, &sn, &cs);
+      r = mag * cs;
+      q = mag * sn;
+    }
+    re[fi][k] = r;
+    im[fi][k] = q;
+  }
+  __syncthreads();
+  const int n = n0 + threadIdx.x;
+  if (n >= 480 * Tmax) return;
+  float y = 0.f;
+  if (n < 480 * T) {
+    const int f_hi = (n + 8) / 4;
+    float acc = 0.f, env = 0.f;
+#pragma unroll
+    for (int d = 3; d >= 0; --d) {
+      const int f = f_hi - d;
+      if (f < 0 || f >= F) continue;
+      const int j = n + 8 - 4 * f;
+      const int fi = f - f_lo;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v = fmaf(re[fi][k], tb.cr[k][j], fmaf(im[fi][k], tb.ci[k][j], v));
+      acc += v;
+      env += tb.w2[j];
+    }
+    y = acc / env;
+    y = fminf(fmaxf(y, -limit), limit);
+  }
+  wav[(long)b * Lmax + n] = y;
+}
+
+}  // namespace jv
