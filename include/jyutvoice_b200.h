@@ -102,12 +102,18 @@ int jv_hift_f0(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const floa
  * Uniform(-pi,pi) draw, entry 0 is ignored and treated as 0); noise dev [B,9,480*Tmax] (the
  * randn_like draw) -> s dev [B,480*Tmax].  The caller draws the RNG exactly as the reference does. */
 int jv_hift_source(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* f0,
-                   const float* phase, const float* noise, float* s, void* stream);
+                   const float* phase, const float* noise, float* s, void* ws, size_t ws_bytes, void* stream);
 /* HiFTGenerator.decode(x=mel, s) (generator.py:396-432): -> wav dev [B,480*Tmax]; samples beyond
  * 480*len_b are 0.  Each utterance is decoded with its own zero boundary, i.e. equals the
  * reference's unpadded batch-1 call. */
 int jv_hift_decode(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* mel,
                    const float* s, float* wav, void* ws, size_t ws_bytes, void* stream);
+
+/* Profiling of the dominant kernel (the tcgen05 GEMM): between begin and end every launch of it is
+ * bracketed by CUDA events on its own stream.  end() synchronises the device and returns the summed
+ * kernel time, the summed algorithmic FLOPs (valid frames only) and the launch count. */
+int jv_profile_begin(void);
+int jv_profile_end(double* kernel_ms, double* algo_flops, int64_t* launches);
 
 /* Test hook: C[M,N] = A[M,K] * W[N,K]^T (+bias) through the same GEMM engine the handles use
  * (precision selects fp32 FFMA or bf16 tcgen05).  A, W, bias, C: dev fp32; operands are rounded to

@@ -1,4 +1,5 @@
 """jyutvoice_b200: B200-native (sm_100a) CFM + HiFT hot path behind the reference's Python API."""
 from .flow_matching import CausalConditionalCFM, CausalConditionalDecoder  # noqa: F401
+from .hifigan import HiFTGenerator, ConvRNNF0Predictor  # noqa: F401
 
-__all__ = ["CausalConditionalCFM", "CausalConditionalDecoder"]
+__all__ = ["CausalConditionalCFM", "CausalConditionalDecoder", "HiFTGenerator", "ConvRNNF0Predictor"]

@@ -44,8 +44,10 @@ SIGNATURES = {
     "jv_hift_finalize": (c_int, [c_void_p]),
     "jv_hift_workspace_bytes": (c_size_t, [c_void_p, c_int, P_i32]),
     "jv_hift_f0": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "jv_hift_source": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jv_hift_source": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "jv_hift_decode": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "jv_profile_begin": (c_int, []),
+    "jv_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "jv_test_gemm": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -20,6 +20,35 @@ int jv_version(void) { return 1; }
 const char* jv_last_error(void) { return g_last_error.c_str(); }
 uint64_t jv_launch_count(void) { return g_launch_count.load(); }
 
+int jv_profile_begin(void) {
+  JV_API_BEGIN
+  ProfileState& ps = profile_state();
+  for (cudaEvent_t e : ps.ev) cudaEventDestroy(e);
+  ps.ev.clear();
+  ps.flops = 0.0;
+  ps.on = true;
+  JV_API_END
+}
+
+int jv_profile_end(double* kernel_ms, double* algo_flops, int64_t* launches) {
+  JV_API_BEGIN
+  ProfileState& ps = profile_state();
+  ps.on = false;
+  JV_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < ps.ev.size(); i += 2) {
+    float t = 0.f;
+    JV_CUDA(cudaEventElapsedTime(&t, ps.ev[i], ps.ev[i + 1]));
+    ms += t;
+  }
+  if (kernel_ms) *kernel_ms = ms;
+  if (algo_flops) *algo_flops = ps.flops;
+  if (launches) *launches = (int64_t)(ps.ev.size() / 2);
+  for (cudaEvent_t e : ps.ev) cudaEventDestroy(e);
+  ps.ev.clear();
+  JV_API_END
+}
+
 int jv_test_gemm(int precision, int M, int N, int K, const float* A, const float* W, const float* bias, float* C, void* stream) {
   try {
     JV_REQUIRE(M > 0 && N > 0 && K > 0 && A && W && C, JV_ERR_INVALID, "bad arguments");

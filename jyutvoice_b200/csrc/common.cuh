@@ -122,7 +122,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float p, float a) {
 // ---------------------------------------------------------------- GEMM-with-taps problem description
 // C[out_row(m), n] = epilogue( sum_s sum_k A_src(s)[m*a_stride + shift_s, k] * W[n, s*K_tap + k] )
 // This one form covers Linear, (causal / dilated / strided) Conv1d and the polyphase ConvTranspose1d.
-constexpr int MAX_TAPS = 16;
+constexpr int MAX_TAPS = 32;
 
 struct GemmDesc {
   // A operands: up to two sources (channel concat, e.g. the U-Net skip), element type = activation type
@@ -154,6 +154,7 @@ struct GemmDesc {
   const float* act2_vec;
   int o_stride, o_off;   // out_row = m * o_stride + o_off
   long o_rows;           // out_row must be < o_rows
+  double algo_flops;     // algorithmic FLOPs of this launch (valid frames, true N and K); profiling only
 };
 
 static inline GemmDesc gemm_desc_default() {
@@ -166,3 +167,17 @@ static inline GemmDesc gemm_desc_default() {
 }
 
 }  // namespace jv
+
+// C-ABI wrappers: no exception crosses the boundary
+#define JV_API_BEGIN try {
+#define JV_API_END                                   \
+  }                                                  \
+  catch (const jv::Error& e) {                       \
+    jv::set_last_error(e.what());                    \
+    return e.code;                                   \
+  }                                                  \
+  catch (const std::exception& e) {                  \
+    jv::set_last_error(e.what());                    \
+    return JV_ERR_CUDA;                              \
+  }                                                  \
+  return JV_OK;

@@ -215,6 +215,7 @@ struct FwdCtx {
   jv_estimator* h;
   EstBuffers b;
   int M, M_alloc, R, Tmax_len;  // Tmax_len: longest row (attention grid)
+  long valid_frames;            // sum of row lengths (algorithmic FLOP accounting)
   const float* temb_step;       // temb rows of the current step: [*, 14, 256]
   cudaStream_t st;
 };
@@ -239,6 +240,7 @@ static GemmDesc conv_desc(const FwdCtx& c, const PackedW& w, const void* A0p, co
   g.bias = w.bias;
   g.frame_row = c.b.frame_row;
   g.o_rows = c.M_alloc;
+  g.algo_flops = 2.0 * (double)c.valid_frames * w.N * w.n_taps * w.K_tap;
   return g;
 }
 
@@ -415,18 +417,7 @@ static size_t workspace_bytes(const jv_estimator* h, int R, const int32_t* lens,
 }  // namespace jv
 
 // =========================================================================================== C ABI
-#define JV_API_BEGIN try {
-#define JV_API_END                                   \
-  }                                                  \
-  catch (const jv::Error& e) {                       \
-    jv::set_last_error(e.what());                    \
-    return e.code;                                   \
-  }                                                  \
-  catch (const std::exception& e) {                  \
-    jv::set_last_error(e.what());                    \
-    return JV_ERR_CUDA;                              \
-  }                                                  \
-  return JV_OK;
+
 
 extern "C" {
 
@@ -498,6 +489,8 @@ int jv_estimator_forward(jv_estimator* h, int R, int Tmax, const int32_t* lens_h
   c.b = carve(ar, h->eng, L.M_alloc, R, R);
   int* lens_dev = ar.alloc<int>(R);
   c.M = L.M; c.M_alloc = L.M_alloc; c.R = R; c.Tmax_len = tmax_len;
+  c.valid_frames = 0;
+  for (int r = 0; r < R; ++r) c.valid_frames += L.row_len[r];
   c.st = (cudaStream_t)stream;
   c.temb_step = c.b.temb;
   std::vector<int> tidx(R);
@@ -538,6 +531,8 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
   c.b = carve(ar, h->eng, L.M_alloc, R, 64);
   int* lens_dev = ar.alloc<int>(R);
   c.M = L.M; c.M_alloc = L.M_alloc; c.R = R; c.Tmax_len = tmax_len;
+  c.valid_frames = 0;
+  for (int r = 0; r < R; ++r) c.valid_frames += L.row_len[r];
   c.st = (cudaStream_t)stream;
   c.temb_step = c.b.temb;
   std::vector<int> tidx(R, 0);

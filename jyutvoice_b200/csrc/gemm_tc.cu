@@ -33,6 +33,11 @@ const CUtensorMap& TmapCache::get(const void* ptr, long inner_elems, long rows, 
   return maps.emplace(key, m).first->second;
 }
 
+ProfileState& profile_state() {
+  static ProfileState s;
+  return s;
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 bool gemm_tc_supported(const GemmDesc& g) {
@@ -69,8 +74,21 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   const CUtensorMap& tA1 = g.A[1] ? cache.get(g.A[1], g.K_tap, g.a_rows[1], g.lda[1], tc::BLOCK_M) : tA0;
   const CUtensorMap& tW = cache.get(g.W, Ktot, g.N, Ktot, block_n);
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  ProfileState& ps = profile_state();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ps.on) {
+    JV_CUDA(cudaEventCreate(&e0));
+    JV_CUDA(cudaEventCreate(&e1));
+    JV_CUDA(cudaEventRecord(e0, st));
+  }
   tc::gemm_taps_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(tA0, tA1, tW, g, block_n, n_tiles_n, num_tiles);
   JV_LAUNCHED();
+  if (ps.on) {
+    JV_CUDA(cudaEventRecord(e1, st));
+    ps.ev.push_back(e0);
+    ps.ev.push_back(e1);
+    ps.flops += g.algo_flops;
+  }
 }
 
 }  // namespace jv

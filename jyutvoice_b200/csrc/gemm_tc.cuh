@@ -319,6 +319,13 @@ struct TmapCache {
 };
 
 // True when the tcgen05 kernel can run this problem (else the caller uses the FFMA engine).
+struct ProfileState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  double flops = 0.0;
+};
+ProfileState& profile_state();
+
 bool gemm_tc_supported(const GemmDesc& g);
 void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream_t st);
 

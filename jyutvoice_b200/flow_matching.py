@@ -152,8 +152,9 @@ class CausalConditionalCFM(nn.Module):
         return self._noise_dev
 
     @torch.inference_mode()
-    def forward(self, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False):
-        """Reference signature (flow_matching.py:357-401) -> (mel fp32 [B,80,T], None)."""
+    def forward(self, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False, lengths=None):
+        """Reference signature (flow_matching.py:357-401) -> (mel fp32 [B,80,T], None).
+        `lengths` (host ints) may replace `mask` to skip the device->host read of the mask."""
         if streaming:
             raise NotImplementedError("streaming chunk masks are outside this path")
         if not isinstance(self.estimator, CausalConditionalDecoder):
@@ -162,7 +163,12 @@ class CausalConditionalCFM(nn.Module):
         B, _, T = mu.shape
         if T > self.rand_noise.shape[2]:
             raise ValueError(f"{T} frames exceed the {self.rand_noise.shape[2]}-frame noise bank")
-        lens = _lens_from_mask(mask)
+        if lengths is not None:
+            lens = [int(v) for v in lengths]
+            if len(lens) != B or min(lens) < 1 or max(lens) > T:
+                raise ValueError("lengths must hold one value in [1, T] per utterance")
+        else:
+            lens = _lens_from_mask(mask)
         h = self.estimator.handle(dev)
         L = _lib.lib()
         lens_c = _lib.i32_array(lens)

@@ -1,0 +1,232 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI via the Python mirrors, against
+ (1) golden vectors made by the unmodified reference, (2) the oracle on the same seeded inputs,
+ (3) size-independent properties at BASELINE.json's sizes.
+Tolerances (north_star): fp32 mode mel max-abs <= 1e-3, waveform SNR >= 60 dB; integer indexing exact.
+bf16 mode ("stated looser bound", BASELINE.md section 5, frozen from B200 measurements): mel max-abs <= 1e-1 and
+rel-RMS <= 2e-2; waveform SNR >= 40 dB at decode(x, s)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, snr_db
+
+pytestmark = pytest.mark.gpu
+
+FP32_MEL_TOL = 1e-3
+BF16_MEL_TOL = 1e-1
+BF16_MEL_RELRMS = 2e-2
+FP32_SNR = 60.0
+BF16_SNR = 40.0
+
+
+def rel_rms(x, ref):
+    return float((x - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+
+
+@pytest.fixture(scope="module")
+def cfms(est_sd):
+    from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder
+    out = {}
+    for prec in ("fp32", "bf16"):
+        cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision=prec))
+        cfm.load_state_dict(est_sd, strict=True)
+        out[prec] = cfm.cuda()
+    return out
+
+
+@pytest.fixture(scope="module")
+def hifts(hift_sd, hift_sd_voiced):
+    from jyutvoice_b200 import HiFTGenerator
+    out = {}
+    for prec in ("fp32", "bf16"):
+        for tag, sd in (("unvoiced", hift_sd), ("voiced", hift_sd_voiced)):
+            h = HiFTGenerator(precision=prec)
+            h.load_state_dict(sd, strict=True)
+            out[(prec, tag)] = h.cuda()
+    return out
+
+
+# ------------------------------------------------------------------------------ GEMM engines
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 256, 256), (1000, 1536, 256), (777, 80, 256), (2048, 256, 1024), (515, 64, 128)])
+def test_gemm_engine(prec, shape):
+    from jyutvoice_b200 import _lib
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    C = torch.full((M, N), float("nan"), device="cuda")
+    p = lambda z: ctypes.c_void_p(z.data_ptr())
+    _lib.check(_lib.lib().jv_test_gemm(_lib.PREC[prec], M, N, K, p(A), p(W), p(b), p(C), None))
+    if prec == "bf16":
+        ref = A.bfloat16().double() @ W.bfloat16().double().T + b.double()
+    else:
+        ref = A.double() @ W.double().T + b.double()
+    assert (C.double() - ref).abs().max().item() <= 5e-5
+
+
+# ------------------------------------------------------------------------------ estimator / CFM
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_estimator_forward_golden(cfms, prec):
+    from oracle.make_golden import est_inputs
+    g = np.load(os.path.join(GOLDEN, "estimator_fwd.npz"))
+    x, mask, mu, t, spks, cond = est_inputs(int(g["seed"]), int(g["R"]), int(g["T"]), list(g["lens"]))
+    v = cfms[prec].estimator(x.cuda(), mask.cuda(), mu.cuda(), t.cuda(), spks.cuda(), cond.cuda()).cpu()
+    ref = torch.from_numpy(g["out"])
+    err = (v - ref).abs().max().item()
+    if prec == "fp32":
+        assert err <= 1e-4
+    else:
+        assert err <= BF16_MEL_TOL and rel_rms(v, ref) <= BF16_MEL_RELRMS
+    assert float(v[1, :, 20:].abs().max()) == 0.0  # padded frames exactly zero, as in the reference
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["cfm_T33_n4", "cfm_T50_n10", "cfm_T40_n5_cond"])
+def test_cfm_golden(cfms, prec, name):
+    from oracle.make_golden import cfm_inputs
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    T, n = int(g["T"]), int(g["n_timesteps"])
+    mu, spks = cfm_inputs(int(g["seed"]), T)
+    cond = torch.zeros(1, 80, T)
+    temperature = 1.0
+    if name.endswith("cond"):
+        cond[:, :, :12] = torch.randn(1, 80, 12, generator=torch.Generator().manual_seed(90))
+        temperature = float(g["temperature"])
+    mel, none = cfms[prec](mu.cuda(), torch.ones(1, 1, T).cuda(), n, temperature, spks.cuda(), cond.cuda())
+    assert none is None and mel.dtype == torch.float32
+    ref = torch.from_numpy(g["out"])
+    err = (mel.cpu() - ref).abs().max().item()
+    if prec == "fp32":
+        assert err <= FP32_MEL_TOL
+    else:
+        assert err <= BF16_MEL_TOL and rel_rms(mel.cpu(), ref) <= BF16_MEL_RELRMS
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_cfm_ragged_batch_equals_batch1_oracle(cfms, prec, est_sd, noise_bank):
+    """The reference is batch-1 only; a batch must give, per utterance, the unpadded B=1 answer."""
+    from oracle import estimator as oe
+    lens = [41, 1, 17, 30]
+    B = len(lens)
+    g = torch.Generator().manual_seed(77)
+    mu = torch.randn(B, 80, max(lens), generator=g)
+    spks = torch.randn(B, 80, generator=g)
+    mask = torch.zeros(B, 1, max(lens))
+    for i, l in enumerate(lens):
+        mask[i, 0, :l] = 1
+    mel, _ = cfms[prec](mu.cuda(), mask.cuda(), 3, 1.0, spks.cuda(), None)
+    mel = mel.cpu()
+    with torch.no_grad():
+        ref = oe.cfm_forward_batch(est_sd, noise_bank, mu, lens, 3, 1.0, spks, None)
+    tol = FP32_MEL_TOL if prec == "fp32" else BF16_MEL_TOL
+    assert (mel - ref).abs().max().item() <= tol
+    for i, l in enumerate(lens):
+        if l < max(lens):
+            assert float(mel[i, :, l:].abs().max()) == 0.0
+
+
+def test_cfm_batch_invariance_full_size(cfms):
+    """BASELINE config 5 shape (64 x ~300 frames, 10 NFE, bf16): an utterance's mel must not depend on
+    what else is in the batch (rows are independent), and the run is deterministic."""
+    cfm = cfms["bf16"]
+    g = torch.Generator().manual_seed(5)
+    B, T = 64, 330
+    lens = torch.randint(270, 331, (B,), generator=g).tolist()
+    mu = torch.randn(B, 80, T, generator=g).cuda()
+    spks = torch.randn(B, 80, generator=g).cuda()
+    mel, _ = cfm(mu, None, 10, 1.0, spks, None, lengths=lens)
+    mel2, _ = cfm(mu, None, 10, 1.0, spks, None, lengths=lens)
+    assert torch.equal(mel, mel2)
+    assert torch.isfinite(mel).all()
+    for i in (0, 37, 63):
+        one, _ = cfm(mu[i:i + 1, :, : lens[i]].contiguous(), None, 10, 1.0, spks[i:i + 1], None, lengths=[lens[i]])
+        assert torch.equal(one[0], mel[i, :, : lens[i]])
+
+
+def test_cfm_errors(cfms):
+    cfm = cfms["fp32"]
+    mu = torch.zeros(2, 80, 10).cuda()
+    with pytest.raises(ValueError):
+        cfm(mu, None, 2, spks=torch.zeros(2, 80).cuda(), lengths=[10, 11])
+    with pytest.raises(ValueError):
+        cfm(mu, None, 2, spks=torch.zeros(2, 80).cuda(), lengths=[10, 0])
+    with pytest.raises(NotImplementedError):
+        cfm(mu, torch.ones(2, 1, 10).cuda(), 2, spks=torch.zeros(2, 80).cuda(), streaming=True)
+
+
+# ------------------------------------------------------------------------------ HiFT
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["unvoiced", "voiced"])
+def test_hift_golden(hifts, prec, tag):
+    from oracle import hift as oh
+    from oracle.make_golden import hift_mel
+    hift = hifts[(prec, tag)]
+    g = np.load(os.path.join(GOLDEN, f"hift_{tag}.npz"))
+    B, T = int(g["B"]), int(g["T"])
+    mel = hift_mel(int(g["seed"]), B, T)
+    f0 = hift.predict_f0(mel.cuda()).cpu()
+    f0_ref = torch.from_numpy(g["f0"])
+    assert (f0 - f0_ref).abs().max().item() <= (1e-3 if prec == "fp32" else 5e-2) * max(1.0, float(f0_ref.max()) / 100)
+    rng = oh.draw_source_rng(B, T * 480, torch.Generator().manual_seed(int(g["rng_seed"])))
+    s_ref = torch.from_numpy(g["s"])
+    s = hift.source(f0_ref.cuda(), rng).cpu()
+    assert (s - s_ref).abs().max().item() <= 1e-5  # fp64 phase prefix == torch's CPU cumsum
+    wav = hift.decode(mel.cuda(), s_ref.cuda()).cpu()
+    assert wav.shape == (B, 480 * T)
+    assert snr_db(torch.from_numpy(g["wav_decode"]), wav) >= (FP32_SNR if prec == "fp32" else BF16_SNR)
+    if prec == "fp32":
+        wav_i, s_i = hift.inference(mel.cuda(), rng=rng)
+        assert s_i.shape == (B, 1, 480 * T)
+        assert snr_db(torch.from_numpy(g["wav_inference"]), wav_i.cpu()) >= FP32_SNR
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_hift_ragged_equals_unpadded(hifts, prec, hift_sd):
+    """Naive zero padding leaks ~41 dB backwards through the non-causal convs;
+    every utterance of a ragged batch must equal its own unpadded decode."""
+    from oracle import hift as oh
+    hift = hifts[(prec, "unvoiced")]
+    g = torch.Generator().manual_seed(8)
+    lens = [23, 9, 1, 16]
+    B, T = len(lens), max(lens)
+    mel = torch.randn(B, 80, T, generator=g) * 2 - 5
+    s = torch.randn(B, 1, 480 * T, generator=g) * 0.05
+    wav = hift.decode(mel.cuda(), s.cuda(), lengths=lens).cpu()
+    for i, l in enumerate(lens):
+        with torch.no_grad():
+            ref = oh.decode(hift_sd, mel[i:i + 1, :, :l], s[i:i + 1, :, : 480 * l])
+        assert snr_db(ref, wav[i:i + 1, : 480 * l]) >= (FP32_SNR if prec == "fp32" else BF16_SNR)
+        assert float(wav[i, 480 * l:].abs().sum()) == 0.0
+
+
+def test_hift_full_size_properties(hifts):
+    """BASELINE config 3 shape (32 mels of 80 x 500): finite, clamped, deterministic, batch-invariant."""
+    hift = hifts[("bf16", "unvoiced")]
+    g = torch.Generator().manual_seed(3)
+    mel = (torch.randn(32, 80, 500, generator=g) * 2 - 5).cuda()
+    rng = {"phase": torch.zeros(32, 9, 1), "noise": torch.randn(32, 9, 480 * 500, generator=g)}
+    wav, s = hift.inference(mel, rng=rng)
+    wav2, _ = hift.inference(mel, rng=rng)
+    assert torch.equal(wav, wav2)
+    assert torch.isfinite(wav).all() and float(wav.abs().max()) <= 0.99 + 1e-6
+    one, _ = hift.inference(mel[5:6], rng={"phase": rng["phase"][5:6], "noise": rng["noise"][5:6]})
+    assert torch.equal(one[0], wav[5])
+
+
+def test_inference_draws_rng_like_the_reference(hifts):
+    """Default rng: Uniform on CPU, randn on the device, in the reference's order (generator.py:155-158,171,235)."""
+    hift = hifts[("fp32", "unvoiced")]
+    mel = (torch.randn(1, 80, 12) * 2 - 5).cuda()
+    torch.manual_seed(123)
+    w1, s1 = hift.inference(mel)
+    torch.manual_seed(123)
+    w2, s2 = hift.inference(mel)
+    assert torch.equal(w1, w2) and torch.equal(s1, s2)
+    torch.manual_seed(124)
+    w3, _ = hift.inference(mel)
+    assert not torch.equal(w1, w3)

@@ -116,9 +116,64 @@ def estimator_checks():
         del cfm, est
 
 
+def hift_checks():
+    from oracle import weights, hift as oh
+    from oracle.make_golden import hift_mel
+    from jyutvoice_b200 import HiFTGenerator
+    from conftest import snr_db
+    GOLD = os.path.join(ROOT, "tests", "golden")
+    for prec in ("fp32", "bf16"):
+        for tag, f0b in (("unvoiced", None), ("voiced", 200.0)):
+            section(f"hift {prec} {tag}")
+            sd = weights.make_hift_state_dict(f0_bias=f0b)
+            hift = HiFTGenerator(precision=prec)
+            hift.load_state_dict(sd, strict=True)
+            hift = hift.cuda()
+            g = np.load(os.path.join(GOLD, f"hift_{tag}.npz"))
+            B, T = int(g["B"]), int(g["T"])
+            mel = hift_mel(int(g["seed"]), B, T)
+            f0 = hift.predict_f0(mel.cuda()).cpu()
+            f0r = torch.from_numpy(g["f0"])
+            print(f"f0: max_abs={(f0-f0r).abs().max().item():.3e} ref_max={f0r.abs().max().item():.3f}", flush=True)
+            rng = oh.draw_source_rng(B, T * 480, torch.Generator().manual_seed(int(g["rng_seed"])))
+            s = hift.source(f0r.cuda(), rng).cpu()
+            sr = torch.from_numpy(g["s"])
+            print(f"source (golden f0): max_abs={(s-sr).abs().max().item():.3e}", flush=True)
+            wav = hift.decode(mel.cuda(), sr.cuda()).cpu()
+            wr = torch.from_numpy(g["wav_decode"])
+            print(f"decode(x, s_golden): snr={snr_db(wr, wav):.1f} dB max_abs={(wav-wr).abs().max().item():.3e} nan={torch.isnan(wav).sum().item()}", flush=True)
+            wav_i, s_i = hift.inference(mel.cuda(), rng=rng)
+            wi = torch.from_numpy(g["wav_inference"])
+            print(f"inference(rng shared): snr={snr_db(wi, wav_i.cpu()):.1f} dB s_max_abs={(s_i.cpu()-sr).abs().max().item():.3e}", flush=True)
+            # ragged batch: each utterance must equal its own unpadded oracle call
+            lens = [30, 19]
+            melr = mel.clone()
+            melr[1, :, 19:] = 0
+            sr2 = sr.clone()
+            wav_r = hift.decode(melr.cuda(), sr2.cuda(), lengths=lens).cpu()
+            with torch.no_grad():
+                ref1 = oh.decode(sd, mel[1:2, :, :19], sr[1:2, :, :19 * 480])
+            print(f"ragged decode utt1 (T=19 of 30): snr={snr_db(ref1, wav_r[1:2, :19*480]):.1f} dB tail_max={wav_r[1, 19*480:].abs().max().item():.1e} "
+                  f"utt0 snr={snr_db(wr[0:1], wav_r[0:1]):.1f}", flush=True)
+            if prec == "bf16" and tag == "unvoiced":
+                B, T = 16, 300
+                melb = (torch.randn(B, 80, T) * 2 - 5).cuda()
+                hift.inference(melb)
+                torch.cuda.synchronize(); t0 = time.time()
+                hift.inference(melb)
+                torch.cuda.synchronize(); dt = time.time() - t0
+                print(f"B=16 T=300 hift bf16: {dt*1e3:.1f} ms -> {B*T/50/dt:.1f} audio-s/s (HiFT only)", flush=True)
+            del hift
+
+
 if __name__ == "__main__":
+    which = sys.argv[1:] or ["gemm", "estimator", "hift"]
     print(torch.cuda.get_device_name(0), torch.__version__)
-    section("gemm")
-    run(gemms)
-    run(estimator_checks)
+    if "gemm" in which:
+        section("gemm")
+        run(gemms)
+    if "estimator" in which:
+        run(estimator_checks)
+    if "hift" in which:
+        run(hift_checks)
     print("launches", _lib.lib().jv_launch_count())
