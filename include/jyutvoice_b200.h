@@ -115,6 +115,12 @@ int jv_hift_decode(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const 
 int jv_profile_begin(void);
 int jv_profile_end(double* kernel_ms, double* algo_flops, int64_t* launches);
 
+/* Micro-benchmark hook: average milliseconds of one tcgen05 GEMM launch, C[M,N] = A[M,K] W[N,K]^T over `taps`
+ * shifted taps (K per tap), timed with CUDA events over `iters` launches after 3 warm-ups.
+ * mode bits: 1 = fp32 residual in + fp32 out, 2 = GELU, 4 = LayerNorm+Mish before the output, 8 = second LayerNorm output,
+ * 16 = bf16 output.  Buffers are allocated and freed inside. */
+int jv_bench_gemm(int M, int N, int K_tap, int taps, int mode, int iters, double* ms_out);
+
 /* Test hook: C[M,N] = A[M,K] * W[N,K]^T (+bias) through the same GEMM engine the handles use
  * (precision selects fp32 FFMA or bf16 tcgen05).  A, W, bias, C: dev fp32; operands are rounded to
  * bf16 inside when precision == JV_PREC_BF16. */

@@ -48,6 +48,7 @@ SIGNATURES = {
     "jv_hift_decode": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "jv_profile_begin": (c_int, []),
     "jv_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
+    "jv_bench_gemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_double)]),
     "jv_test_gemm": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -49,6 +49,54 @@ int jv_profile_end(double* kernel_ms, double* algo_flops, int64_t* launches) {
   JV_API_END
 }
 
+int jv_bench_gemm(int M, int N, int K_tap, int taps, int mode, int iters, double* ms_out) {
+  JV_API_BEGIN
+  JV_REQUIRE(M > 0 && N > 0 && K_tap > 0 && taps > 0 && taps <= MAX_TAPS && iters > 0 && ms_out, JV_ERR_INVALID, "bad arguments");
+  int dev = 0;
+  JV_CUDA(cudaGetDevice(&dev));
+  Engine eng;
+  eng.init(dev, JV_PREC_BF16);
+  const int Mp = round_up(M, 128);
+  void *A, *W, *OA, *OL;
+  float *R, *OF, *vec;
+  JV_CUDA(cudaMalloc(&A, (size_t)Mp * K_tap * 2));
+  JV_CUDA(cudaMalloc(&W, (size_t)N * K_tap * taps * 2));
+  JV_CUDA(cudaMalloc(&OA, (size_t)Mp * N * 2));
+  JV_CUDA(cudaMalloc(&OL, (size_t)Mp * N * 2));
+  JV_CUDA(cudaMalloc(&R, (size_t)Mp * N * 4));
+  JV_CUDA(cudaMalloc(&OF, (size_t)Mp * N * 4));
+  JV_CUDA(cudaMalloc(&vec, (size_t)N * 4));
+  JV_CUDA(cudaMemset(A, 0, (size_t)Mp * K_tap * 2));
+  JV_CUDA(cudaMemset(W, 0, (size_t)N * K_tap * taps * 2));
+  JV_CUDA(cudaMemset(R, 0, (size_t)Mp * N * 4));
+  JV_CUDA(cudaMemset(vec, 0, (size_t)N * 4));
+  GemmDesc g = gemm_desc_default();
+  g.A[0] = A; g.lda[0] = K_tap; g.a_rows[0] = Mp;
+  g.n_taps = taps; g.K_tap = K_tap;
+  for (int t = 0; t < taps; ++t) g.tap_shift[t] = t - (taps - 1);
+  g.W = W; g.M = M; g.N = N; g.bias = vec; g.o_rows = Mp;
+  if (mode & 1) { g.resid = R; g.ldr = N; g.out_f32 = OF; g.ldo = N; }
+  if (mode & 2) g.act = ACT_GELU;
+  if (mode & 4) { g.ln1_gamma = vec; g.ln1_beta = vec; g.act = ACT_MISH; }
+  if (mode & 8) { g.ln2_gamma = vec; g.ln2_beta = vec; g.out_ln = OL; g.ldo3 = N; }
+  if (mode & 16) { g.out_act = OA; g.ldo2 = N; }
+  JV_REQUIRE(gemm_tc_supported(g), JV_ERR_INVALID, "shape not supported by the tcgen05 engine");
+  cudaEvent_t e0, e1;
+  JV_CUDA(cudaEventCreate(&e0));
+  JV_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) eng.gemm(g, 0);
+  JV_CUDA(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) eng.gemm(g, 0);
+  JV_CUDA(cudaEventRecord(e1, 0));
+  JV_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  JV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(A); cudaFree(W); cudaFree(OA); cudaFree(OL); cudaFree(R); cudaFree(OF); cudaFree(vec);
+  JV_API_END
+}
+
 int jv_test_gemm(int precision, int M, int N, int K, const float* A, const float* W, const float* bias, float* C, void* stream) {
   try {
     JV_REQUIRE(M > 0 && N > 0 && K > 0 && A && W && C, JV_ERR_INVALID, "bad arguments");

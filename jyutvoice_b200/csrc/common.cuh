@@ -136,22 +136,36 @@ struct GemmDesc {
   int K_tap;           // K per tap (same for all taps)
   const void* W;       // [N, n_taps*K_tap] K-major, activation type
   int M, N;
-  // epilogue
+  // epilogue, in this order (every step optional):
+  //   v = acc + bias[n]
+  //   v = LN1(v) over the N channels of the row (gamma/beta; needs N == 256)
+  //   v = act(v)
+  //   v += add_row[row_tidx[frame_row[row]] * add_row_stride + n]      (time embedding)
+  //   v = frame_row[row] >= 0 ? v : 0                                   (padding mask)
+  //   v += resid[row, n]                                                (fp32 residual / skip branch)
+  //   out_f32[row, n] = v ; out_act[row, n] = act2(v) ; out_ln[row, n] = mask(LN2(v))
   const float* bias;   // [N] or null
-  const float* resid;  // fp32 [*, ldr] indexed by out_row, or null
-  int ldr;
+  const float* ln1_gamma;
+  const float* ln1_beta;
   int act;
   float act_param;
   const float* act_vec;
-  const int* frame_row;  // [rows] >= 0 valid, < 0 -> write 0; null = all valid (indexed by out_row)
-  float out_scale;
-  int accumulate;        // out_f32 = out_f32 + scale * v  (fp32 output only)
+  const float* add_row;
+  const int* row_tidx;
+  int add_row_stride;
+  const int* frame_row;  // [rows] >= 0 valid (value = utterance row), < 0 -> 0; null = all valid (indexed by out_row)
+  const float* resid;    // fp32 [*, ldr] indexed by out_row, or null
+  int ldr;
   float* out_f32;        // optional fp32 output [*, ldo]
   void* out_act;         // optional activation-typed output [*, ldo2]
   int ldo, ldo2;
-  int act2;              // activation applied to the out_act copy only (after everything else)
+  int act2;              // activation applied to the out_act copy only
   float act2_param;
   const float* act2_vec;
+  const float* ln2_gamma;
+  const float* ln2_beta;
+  void* out_ln;          // activation-typed LN2 output [*, ldo3]
+  int ldo3;
   int o_stride, o_off;   // out_row = m * o_stride + o_off
   long o_rows;           // out_row must be < o_rows
   double algo_flops;     // algorithmic FLOPs of this launch (valid frames, true N and K); profiling only
@@ -161,7 +175,6 @@ static inline GemmDesc gemm_desc_default() {
   GemmDesc g;
   memset(&g, 0, sizeof(g));
   g.a_stride = 1;
-  g.out_scale = 1.f;
   g.o_stride = 1;
   return g;
 }

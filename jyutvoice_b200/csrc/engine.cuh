@@ -1,8 +1,11 @@
 // Precision-dispatching GEMM engine shared by the estimator and HiFT handles.
+//   JV_PREC_BF16: the fused tcgen05 kernel (gemm_tc.cuh) runs the whole epilogue, LayerNorms included.
+//   JV_PREC_FP32: the same GemmDesc is lowered to the FFMA GEMM + row-wise LayerNorm kernels (exact fp32 math).
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "kernels.cuh"
 
 namespace jv {
 
@@ -11,6 +14,8 @@ struct Engine {
   int precision = JV_PREC_FP32;
   int num_sms = 148;
   TmapCache tmaps;
+  float* scratch = nullptr;  // fp32 [scratch_rows, 256]: pre-LN values when a fused desc is lowered
+  long scratch_rows = 0;
   bool is_bf16() const { return precision == JV_PREC_BF16; }
   size_t act_size() const { return is_bf16() ? 2 : 4; }
 
@@ -28,12 +33,69 @@ struct Engine {
     num_sms = p.multiProcessorCount;
   }
 
+  template <typename TA>
+  void ln_rows(const LnArgs& a, cudaStream_t st) {
+    ln256_kernel<TA><<<cdiv(a.M * 32, 256), 256, 0, st>>>(a);
+    JV_LAUNCHED();
+  }
+
+  // FFMA path: GEMM with the element-wise part of the epilogue, LayerNorms as separate row kernels.
+  template <typename TA>
+  void gemm_lowered(const GemmDesc& g, cudaStream_t st) {
+    if (!g.ln1_gamma && !g.ln2_gamma) {
+      launch_gemm_simt<TA>(g, st);
+      return;
+    }
+    JV_REQUIRE(g.N == 256 && g.o_stride == 1 && g.o_off == 0, JV_ERR_INVALID, "LayerNorm epilogue needs N == 256, dense rows");
+    if (g.ln1_gamma) {
+      JV_REQUIRE(scratch && scratch_rows >= g.M, JV_ERR_STATE, "engine scratch missing");
+      GemmDesc a = g;  // raw conv + bias -> scratch
+      a.ln1_gamma = a.ln1_beta = a.ln2_gamma = a.ln2_beta = nullptr;
+      a.act = ACT_NONE; a.add_row = nullptr; a.frame_row = nullptr; a.resid = nullptr;
+      a.out_f32 = scratch; a.ldo = 256; a.out_act = nullptr; a.out_ln = nullptr;
+      launch_gemm_simt<TA>(a, st);
+      LnArgs l;
+      l.x = scratch; l.ldx = 256;
+      l.gamma = g.ln1_gamma; l.beta = g.ln1_beta;
+      l.act = g.act;
+      l.add_row = g.add_row; l.row_tidx = g.row_tidx; l.add_row_stride = g.add_row_stride;
+      l.add_mat = g.resid; l.ld_add = g.ldr;
+      l.frame_row = g.frame_row;
+      l.out_f32 = g.out_f32; l.ldo = g.ldo;
+      l.out_act = g.out_act; l.ldo2 = g.ldo2;
+      l.M = g.M;
+      JV_REQUIRE(g.act2 == ACT_NONE, JV_ERR_INVALID, "act2 with LN1 is not used on this path");
+      if (g.ln2_gamma && !l.out_f32) { l.out_f32 = scratch; l.ldo = 256; }  // in place: each warp owns its row
+      ln_rows<TA>(l, st);
+    } else {
+      GemmDesc a = g;
+      a.ln2_gamma = a.ln2_beta = nullptr;
+      a.out_ln = nullptr;
+      JV_REQUIRE(g.out_f32 != nullptr, JV_ERR_INVALID, "LN2 needs the fp32 output");
+      launch_gemm_simt<TA>(a, st);
+    }
+    if (g.ln2_gamma) {
+      LnArgs l;
+      const float* src = g.out_f32 ? g.out_f32 : scratch;
+      l.x = src; l.ldx = g.out_f32 ? g.ldo : 256;
+      l.gamma = g.ln2_gamma; l.beta = g.ln2_beta;
+      l.act = ACT_NONE;
+      l.add_row = nullptr; l.row_tidx = nullptr; l.add_row_stride = 0;
+      l.add_mat = nullptr; l.ld_add = 0;
+      l.frame_row = g.frame_row;
+      l.out_f32 = nullptr; l.ldo = 0;
+      l.out_act = g.out_ln; l.ldo2 = g.ldo3;
+      l.M = g.M;
+      ln_rows<TA>(l, st);
+    }
+  }
+
   void gemm(const GemmDesc& g, cudaStream_t st) {
     if (is_bf16()) {
       if (gemm_tc_supported(g)) launch_gemm_tc(g, tmaps, num_sms, st);
-      else launch_gemm_simt<bf16>(g, st);
+      else gemm_lowered<bf16>(g, st);
     } else {
-      launch_gemm_simt<float>(g, st);
+      gemm_lowered<float>(g, st);
     }
   }
 };

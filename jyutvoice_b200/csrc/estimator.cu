@@ -180,7 +180,7 @@ struct EstBuffers {
   float* tsin;   // [nt, 320]
   float* th1;    // [nt, 1024]
   float* th2;    // [nt, 1024]
-  void *A0, *XA, *XB, *SKIP, *H, *QKV, *ATT, *FF;
+  void *A0, *XA, *XB, *SKIP, *H, *LNX, *QKV, *ATT, *FF;
   float *X, *Y, *RES, *V;
 };
 
@@ -200,6 +200,7 @@ static EstBuffers carve(Arena& ar, const Engine& eng, int M_alloc, int R, int nt
   b.XB = ar.alloc<char>((size_t)M_alloc * C * es);
   b.SKIP = ar.alloc<char>((size_t)M_alloc * C * es);
   b.H = ar.alloc<char>((size_t)M_alloc * C * es);
+  b.LNX = ar.alloc<char>((size_t)M_alloc * C * es);
   b.QKV = ar.alloc<char>((size_t)M_alloc * 1536 * es);
   b.ATT = ar.alloc<char>((size_t)M_alloc * 512 * es);
   b.FF = ar.alloc<char>((size_t)M_alloc * 1024 * es);
@@ -244,24 +245,6 @@ static GemmDesc conv_desc(const FwdCtx& c, const PackedW& w, const void* A0p, co
   return g;
 }
 
-static void run_ln(const FwdCtx& c, const float* x, const LNW& ln, bool mish, const float* add_row, const float* add_mat,
-                   float* out_f32, void* out_act) {
-  LnArgs a;
-  a.x = x; a.ldx = C;
-  a.gamma = ln.g; a.beta = ln.b;
-  a.mish = mish ? 1 : 0;
-  a.add_row = add_row; a.row_tidx = c.b.row_tidx; a.add_row_stride = N_RESNET * C;
-  a.add_mat = add_mat; a.ld_add = C;
-  a.frame_row = c.b.frame_row;
-  a.out_f32 = out_f32; a.ldo = C;
-  a.out_act = out_act; a.ldo2 = C;
-  a.M = c.M_alloc;
-  const int blocks = cdiv(c.M_alloc * 32, 256);
-  if (c.h->eng.is_bf16()) ln256_kernel<bf16><<<blocks, 256, 0, c.st>>>(a);
-  else ln256_kernel<float><<<blocks, 256, 0, c.st>>>(a);
-  JV_LAUNCHED();
-}
-
 static void run_attention(const FwdCtx& c) {
   static bool attr = false;
   if (!attr) {
@@ -279,44 +262,64 @@ static void run_attention(const FwdCtx& c) {
   JV_LAUNCHED();
 }
 
-// resnet (decoder.py:110-115) over conv input(s) in0 (+ in1 for the skip concat); result -> X (fp32 stream)
-static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void* in0, const void* in1) {
+static void set_ln1(GemmDesc& g, const LNW& ln, int act) {
+  g.ln1_gamma = ln.g;
+  g.ln1_beta = ln.b;
+  g.act = act;
+}
+static void set_ln2(const FwdCtx& c, GemmDesc& g, const LNW& ln) {
+  g.ln2_gamma = ln.g;
+  g.ln2_beta = ln.b;
+  g.out_ln = c.b.LNX;
+  g.ldo3 = C;
+}
+
+// resnet (decoder.py:110-115) over conv input(s) in0 (+ in1 for the skip concat); result -> X (fp32 stream) and
+// LNX = norm1(X) of the first transformer block.  Three GEMMs, every LayerNorm / Mish / mask / add fused.
+static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void* in0, const void* in1, const LNW& next_ln) {
   Engine& e = c.h->eng;
+  // h = (Mish(LN(conv1(x*m))) + mlp(t)) * m -> H
   GemmDesc g = conv_desc(c, w.c1, in0, in1, 3);
-  g.out_f32 = c.b.Y; g.ldo = C;
+  set_ln1(g, w.ln1, ACT_MISH);
+  g.add_row = c.temb_step + (size_t)layer * C;
+  g.row_tidx = c.b.row_tidx;
+  g.add_row_stride = N_RESNET * C;
+  g.out_act = c.b.H; g.ldo2 = C;
   e.gemm(g, c.st);
+  // res_conv(x*m) -> RES
   g = conv_desc(c, w.res, in0, in1, 1);
   g.out_f32 = c.b.RES; g.ldo = C;
   e.gemm(g, c.st);
-  // h = (Mish(LN(conv1)) + mlp(t)) * mask  -> H (conv2 input)
-  run_ln(c, c.b.Y, w.ln1, true, c.temb_step + (size_t)layer * C, nullptr, nullptr, c.b.H);
+  // x = Mish(LN(conv2(h))) * m + RES -> X ; LNX = norm1(x)
   g = conv_desc(c, w.c2, c.b.H, nullptr, 3);
-  g.out_f32 = c.b.Y; g.ldo = C;
+  set_ln1(g, w.ln2, ACT_MISH);
+  g.resid = c.b.RES; g.ldr = C;
+  g.out_f32 = c.b.X; g.ldo = C;
+  set_ln2(c, g, next_ln);
   e.gemm(g, c.st);
-  // x = Mish(LN(conv2)) * mask + res_conv(x * mask)
-  run_ln(c, c.b.Y, w.ln2, true, nullptr, c.b.RES, c.b.X, nullptr);
 }
 
-// BasicTransformerBlock (transformer.py:355-443); `copy_to`: activation-typed copy of the block output (conv input)
-static void run_tblock(const FwdCtx& c, const TBlockW& w, void* copy_to) {
+// BasicTransformerBlock (transformer.py:355-443).  On entry LNX = norm1(X).  `next_ln`: norm1 of the following
+// block (fused into the FF2 epilogue) or null; `copy_to`: activation-typed copy of the block output (conv input).
+static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, void* copy_to) {
   Engine& e = c.h->eng;
-  run_ln(c, c.b.X, w.n1, false, nullptr, nullptr, nullptr, c.b.H);
-  GemmDesc g = conv_desc(c, w.qkv, c.b.H, nullptr, 1);
+  GemmDesc g = conv_desc(c, w.qkv, c.b.LNX, nullptr, 1);
   g.out_act = c.b.QKV; g.ldo2 = 1536;
   e.gemm(g, c.st);
   run_attention(c);
-  g = conv_desc(c, w.out, c.b.ATT, nullptr, 1);
+  g = conv_desc(c, w.out, c.b.ATT, nullptr, 1);  // x += to_out(attn) ; LNX = norm3(x)
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
+  set_ln2(c, g, w.n3);
   e.gemm(g, c.st);
-  run_ln(c, c.b.X, w.n3, false, nullptr, nullptr, nullptr, c.b.H);
-  g = conv_desc(c, w.ff1, c.b.H, nullptr, 1);
+  g = conv_desc(c, w.ff1, c.b.LNX, nullptr, 1);
   g.act = ACT_GELU;
   g.out_act = c.b.FF; g.ldo2 = 1024;
   e.gemm(g, c.st);
-  g = conv_desc(c, w.ff2, c.b.FF, nullptr, 1);
+  g = conv_desc(c, w.ff2, c.b.FF, nullptr, 1);  // x += ff(norm3(x)) ; LNX = next norm1(x)
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
+  if (next_ln) set_ln2(c, g, *next_ln);
   if (copy_to) { g.out_act = copy_to; g.ldo2 = C; }
   e.gemm(g, c.st);
 }
@@ -325,16 +328,17 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, void* copy_to) {
 static void forward_packed(const FwdCtx& c) {
   jv_estimator* h = c.h;
   Engine& e = h->eng;
+  e.scratch = c.b.Y;
+  e.scratch_rows = c.M_alloc;
   for (int gi = 0; gi < N_RESNET; ++gi) {
     const GroupW& G = h->groups[gi];
-    const void* in0 = gi == 0 ? c.b.A0 : (gi == N_RESNET - 1 ? c.b.XA : c.b.XA);
+    const void* in0 = gi == 0 ? c.b.A0 : (gi == 1 ? c.b.XB : c.b.XA);  // XB: output of the down CausalConv1d
     const void* in1 = gi == N_RESNET - 1 ? c.b.SKIP : nullptr;
-    if (gi == 1) in0 = c.b.XB;  // output of the down CausalConv1d
-    run_resnet(c, G.rn, gi, in0, in1);
+    run_resnet(c, G.rn, gi, in0, in1, G.tb[0].n1);
     for (int j = 0; j < N_TB; ++j) {
       void* copy_to = nullptr;
       if (j == N_TB - 1) copy_to = gi == 0 ? c.b.SKIP : c.b.XA;
-      run_tblock(c, G.tb[j], copy_to);
+      run_tblock(c, G.tb[j], j + 1 < N_TB ? &G.tb[j + 1].n1 : nullptr, copy_to);
     }
     if (gi == 0) {  // x = CausalConv1d(x * mask) (decoder.py:968)
       GemmDesc g = conv_desc(c, h->down_conv, c.b.SKIP, nullptr, 3);
@@ -345,10 +349,10 @@ static void forward_packed(const FwdCtx& c) {
   GemmDesc g = conv_desc(c, h->up_conv, c.b.XA, nullptr, 3);  // decoder.py:1015
   g.out_act = c.b.XB; g.ldo2 = C;
   e.gemm(g, c.st);
-  g = conv_desc(c, h->final_conv, c.b.XB, nullptr, 3);  // final_block
-  g.out_f32 = c.b.Y; g.ldo = C;
+  g = conv_desc(c, h->final_conv, c.b.XB, nullptr, 3);  // final_block: Mish(LN(conv)) * m
+  set_ln1(g, h->final_ln, ACT_MISH);
+  g.out_act = c.b.H; g.ldo2 = C;
   e.gemm(g, c.st);
-  run_ln(c, c.b.Y, h->final_ln, true, nullptr, nullptr, nullptr, c.b.H);
   g = conv_desc(c, h->final_proj, c.b.H, nullptr, 1);
   g.out_f32 = c.b.V; g.ldo = 80;
   e.gemm(g, c.st);

@@ -13,15 +13,12 @@ __device__ __forceinline__ void gemm_epilogue_store(const GemmDesc& g, int m, in
   if (orow >= g.o_rows) return;
   float v = acc;
   if (g.bias) v += __ldg(g.bias + n);
-  if (g.resid) v += g.resid[orow * g.ldr + n];
   v = apply_act(v, g.act, g.act_param, g.act_vec ? __ldg(g.act_vec + n) : 0.f);
-  if (g.frame_row && g.frame_row[orow] < 0) v = 0.f;
-  v *= g.out_scale;
-  if (g.out_f32) {
-    float* p = g.out_f32 + orow * g.ldo + n;
-    if (g.accumulate) v += *p;
-    *p = v;
-  }
+  const int fr = g.frame_row ? g.frame_row[orow] : 0;
+  if (g.add_row && fr >= 0) v += g.add_row[(long)g.row_tidx[fr] * g.add_row_stride + n];
+  if (fr < 0) v = 0.f;
+  if (g.resid) v += g.resid[orow * g.ldr + n];
+  if (g.out_f32) g.out_f32[orow * g.ldo + n] = v;
   if (g.out_act) {
     float w = apply_act(v, g.act2, g.act2_param, g.act2_vec ? __ldg(g.act2_vec + n) : 0.f);
     ((TA*)g.out_act)[orow * g.ldo2 + n] = DT<TA>::from_f(w);

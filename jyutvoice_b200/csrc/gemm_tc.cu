@@ -1,5 +1,5 @@
 // Host side of the tcgen05 GEMM: tensor-map encoding (driver entry point fetched at run time, so the
-// library does not link libcuda), tile-shape choice and launch.
+// library does not link libcuda), tile-shape / pipeline-depth choice and launch.
 #include "gemm_tc.cuh"
 
 namespace jv {
@@ -16,20 +16,23 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-const CUtensorMap& TmapCache::get(const void* ptr, long inner_elems, long rows, long pitch_elems, int box_rows) {
-  TmapKey key{ptr, inner_elems, rows, pitch_elems, box_rows};
+const CUtensorMap& TmapCache::get(const void* ptr, long inner_elems, long rows, long pitch_bytes, int box_inner, int box_rows,
+                                  int kind) {
+  TmapKey key{ptr, inner_elems, rows, pitch_bytes, box_inner, box_rows, kind};
   auto it = maps.find(key);
   if (it != maps.end()) return it->second;
   CUtensorMap m;
   cuuint64_t gdim[2] = {(cuuint64_t)inner_elems, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)pitch_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)tc::BLOCK_K, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapDataType dt = kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = kind == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = get_encode_tiled()(&m, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  JV_REQUIRE(r == CUDA_SUCCESS, JV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%ld rows=%ld pitch=%ld box_rows=%d",
-             (int)r, ptr, inner_elems, rows, pitch_elems, box_rows);
+  JV_REQUIRE(r == CUDA_SUCCESS, JV_ERR_CUDA,
+             "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%ld rows=%ld pitch=%ld box=%dx%d kind=%d", (int)r, ptr, inner_elems, rows,
+             pitch_bytes, box_inner, box_rows, kind);
   return maps.emplace(key, m).first->second;
 }
 
@@ -50,30 +53,51 @@ bool gemm_tc_supported(const GemmDesc& g) {
     if (!aligned16(g.A[s]) || g.lda[s] % 8 != 0 || g.lda[s] < g.K_tap) return false;
   }
   if (!aligned16(g.W)) return false;
-  if (g.bias && !aligned16(g.bias)) return false;
   if (g.resid && (!aligned16(g.resid) || g.ldr % 4 != 0)) return false;
   if (g.out_f32 && (!aligned16(g.out_f32) || g.ldo % 4 != 0)) return false;
   if (g.out_act && (!aligned16(g.out_act) || g.ldo2 % 8 != 0)) return false;
+  if (g.out_ln && (!aligned16(g.out_ln) || g.ldo3 % 8 != 0)) return false;
+  if ((g.ln1_gamma || g.ln2_gamma || g.add_row) && g.N != 256) return false;
+  if (g.ln2_gamma && !g.out_ln) return false;
   return true;
+}
+
+// view of an output-like tensor through (o_stride, o_off): row i of the view = tensor row i*o_stride + o_off
+static const CUtensorMap& out_view(TmapCache& cache, const GemmDesc& g, const void* ptr, int ld, int esize, int kind) {
+  const long view_rows = (g.o_rows - g.o_off + g.o_stride - 1) / g.o_stride;
+  const char* base = (const char*)ptr + (long)g.o_off * ld * esize;
+  return cache.get(base, g.N, view_rows, (long)g.o_stride * ld * esize, 32, 32, kind);
 }
 
 void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
-    JV_CUDA(cudaFuncSetAttribute(tc::gemm_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    JV_CUDA(cudaFuncSetAttribute(tc::gemm_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
     attr_set = true;
   }
-  int block_n = g.N <= 256 ? round_up(g.N, 32) : 256;
-  const int n_tiles_n = cdiv(g.N, block_n);
+  tc::TcParams p;
+  p.block_n = g.N <= 256 ? round_up(g.N, 32) : 256;
+  p.n_tiles_n = cdiv(g.N, p.block_n);
   const int m_tiles = cdiv(g.M, tc::BLOCK_M);
-  const int num_tiles = m_tiles * n_tiles_n;
+  p.num_tiles = m_tiles * p.n_tiles_n;
+  p.b_stage_bytes = round_up(p.block_n * tc::BLOCK_K * 2, 1024);
+  const int fixed = 1024 + tc::EPI_WARPS * tc::EPI_BYTES_PER_WARP + tc::BAR_BYTES;
+  p.stages = (tc::SMEM_LIMIT - fixed) / (tc::A_STAGE_BYTES + p.b_stage_bytes);
+  if (p.stages > tc::MAX_STAGES) p.stages = tc::MAX_STAGES;
+  JV_REQUIRE(p.stages >= 2, JV_ERR_STATE, "not enough shared memory for the GEMM pipeline");
+  const int smem = fixed + p.stages * (tc::A_STAGE_BYTES + p.b_stage_bytes);
   const long Ktot = (long)g.n_taps * g.K_tap;
   if (cache.maps.size() > 4096) cache.maps.clear();  // before the gets: references must stay valid below
-  const CUtensorMap& tA0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], g.lda[0], tc::BLOCK_M);
-  const CUtensorMap& tA1 = g.A[1] ? cache.get(g.A[1], g.K_tap, g.a_rows[1], g.lda[1], tc::BLOCK_M) : tA0;
-  const CUtensorMap& tW = cache.get(g.W, Ktot, g.N, Ktot, block_n);
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  tc::TcMaps tm;
+  tm.a0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], (long)g.lda[0] * 2, tc::BLOCK_K, tc::BLOCK_M, 0);
+  tm.a1 = g.A[1] ? cache.get(g.A[1], g.K_tap, g.a_rows[1], (long)g.lda[1] * 2, tc::BLOCK_K, tc::BLOCK_M, 0) : tm.a0;
+  tm.w = cache.get(g.W, Ktot, g.N, Ktot * 2, tc::BLOCK_K, p.block_n, 0);
+  tm.resid = g.resid ? out_view(cache, g, g.resid, g.ldr, 4, 1) : tm.a0;
+  tm.out_f32 = g.out_f32 ? out_view(cache, g, g.out_f32, g.ldo, 4, 1) : tm.a0;
+  tm.out_act = g.out_act ? out_view(cache, g, g.out_act, g.ldo2, 2, 2) : tm.a0;
+  tm.out_ln = g.out_ln ? out_view(cache, g, g.out_ln, g.ldo3, 2, 2) : tm.a0;
+  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   ProfileState& ps = profile_state();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ps.on) {
@@ -81,7 +105,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
     JV_CUDA(cudaEventCreate(&e1));
     JV_CUDA(cudaEventRecord(e0, st));
   }
-  tc::gemm_taps_tc_kernel<<<grid, tc::NUM_THREADS, tc::SMEM_BYTES, st>>>(tA0, tA1, tW, g, block_n, n_tiles_n, num_tiles);
+  tc::gemm_taps_tc_kernel<<<grid, tc::NUM_THREADS, smem, st>>>(tm, g, p);
   JV_LAUNCHED();
   if (ps.on) {
     JV_CUDA(cudaEventRecord(e1, st));

@@ -1,10 +1,17 @@
 // tcgen05 / TMA / TMEM GEMM-with-taps for sm_100a (bf16 operands, fp32 accumulation in TMEM).
 //
-// One persistent, warp-specialised kernel:
+// One persistent, warp-specialised kernel, 384 threads, one CTA per SM:
 //   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor.2d -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128, N=block_n, K=16)
 //   warp 2        : TMEM allocator (512 columns = 2 accumulator stages of up to 256 fp32 columns)
-//   warps 4..7    : epilogue      (tcgen05.ld 32x32b.x32 -> registers -> bias/residual/act/mask -> global)
+//   warps 4..7    : epilogue group 0 (accumulator stage 0: even tiles of this CTA)
+//   warps 8..11   : epilogue group 1 (accumulator stage 1: odd tiles)
+// Epilogue: one thread owns one output row (TMEM lane).  Per 32-column chunk: tcgen05.ld -> registers ->
+// bias / LayerNorm / activation / time-embedding / mask / residual -> swizzled smem staging -> TMA store.
+// The residual tile arrives by TMA load into the same staging buffer, so all global traffic of the
+// epilogue is coalesced by the TMA engine.  LayerNorm over the 256 channels of a frame is row-local:
+// statistics are taken in extra sweeps over TMEM (which doubles as the scratch for the post-LN value).
+//
 // "Taps" make Conv1d a GEMM without im2col: tap s reads the A tile shifted by tap_shift[s] rows; TMA
 // zero-fills rows outside the tensor, and the packed activation layout keeps >= |shift| zero rows
 // between utterances, which is exactly the conv's zero padding.
@@ -17,12 +24,16 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements: 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;      // 32 KB (block_n <= 256)
-constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_F32_BYTES = 32 * 32 * 4;  // 4 KB: 32 rows x 128 B, SWIZZLE_128B
+constexpr int EPI_B16_BYTES = 32 * 32 * 2;  // 2 KB: 32 rows x 64 B, SWIZZLE_64B
+constexpr int EPI_BYTES_PER_WARP = EPI_F32_BYTES + EPI_B16_BYTES;
+constexpr int BAR_BYTES = 512;
+constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -49,11 +60,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (with a message) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("jyutvoice_b200: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
-      __trap();
+    if ((++polls & 4095u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {
+        printf("jyutvoice_b200: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
+        __trap();
+      }
     }
   }
 }
@@ -64,6 +80,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar,
       ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)tm), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -105,67 +130,188 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
-// Epilogue for 8 consecutive columns of one output row (vectorised global access).
-__device__ __forceinline__ void epilogue8(const GemmDesc& g, long orow, int n, bool row_valid, const uint32_t* acc) {
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[j]);
-  if (g.bias) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-  if (g.resid) {
-    const float4 r0 = *reinterpret_cast<const float4*>(g.resid + orow * g.ldr + n);
-    const float4 r1 = *reinterpret_cast<const float4*>(g.resid + orow * g.ldr + n + 4);
-    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-  }
-  if (g.act != ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], g.act, g.act_param, g.act_vec ? __ldg(g.act_vec + n + j) : 0.f);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = row_valid ? v[j] * g.out_scale : 0.f;
-  if (g.out_f32) {
-    float4* p = reinterpret_cast<float4*>(g.out_f32 + orow * g.ldo + n);
-    if (g.accumulate) {
-      const float4 o0 = p[0], o1 = p[1];
-      v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
-      v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+// ---------------------------------------------------------------- fast epilogue math (bf16 mode only:
+// results are rounded to bf16 or feed bf16 operands, so ~1e-6 absolute error is invisible)
+__device__ __forceinline__ float fast_erf(float x) {
+  // Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float fast_mish(float x) {
+  // x * tanh(softplus(x)) = x * (e^2 + 2e) / (e^2 + 2e + 2), e = exp(x)
+  if (x > 20.f) return x;
+  const float e = __expf(x);
+  const float n = e * (e + 2.0f);
+  return x * __fdividef(n, n + 2.0f);
+}
+__device__ __forceinline__ float apply_act_fast(float v, int act, float p, float a) {
+  switch (act) {
+    case ACT_GELU: return 0.5f * v * (1.f + fast_erf(v * 0.70710678118654752440f));
+    case ACT_ELU: return v > 0.f ? v : __expf(v) - 1.0f;
+    case ACT_LRELU: return v > 0.f ? v : v * p;
+    case ACT_SNAKE: {
+      const float s = __sinf(v * a);
+      return fmaf(__frcp_rn(a + 1e-9f) * s, s, v);
     }
-    p[0] = make_float4(v[0], v[1], v[2], v[3]);
-    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+    case ACT_MISH: return fast_mish(v);
+    case ACT_SILU: return __fdividef(v, 1.f + __expf(-v));
+    default: return v;
   }
-  if (g.out_act) {
-    if (g.act2 != ACT_NONE) {
+}
+
+// ---------------------------------------------------------------- row-chunk helpers: 32 consecutive columns of one row per thread.
+// Every optional epilogue step is its own unswitched loop over the 32 registers, so a feature that is off costs one
+// uniform branch per chunk instead of one per element.  Per-column vectors are read as float4 (same address in every
+// lane -> one broadcast transaction), guarded in groups of 8 columns for N that is not a multiple of 32.
+__device__ __forceinline__ void add_vec32(float (&v)[32], const float* __restrict__ pv, int n_valid) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], g.act2, g.act2_param, g.act2_vec ? __ldg(g.act2_vec + n + j) : 0.f);
+  for (int j8 = 0; j8 < 4; ++j8) {
+    if (j8 * 8 + 8 <= n_valid) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pv + j8 * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(pv + j8 * 8 + 4));
+      v[j8 * 8 + 0] += a.x; v[j8 * 8 + 1] += a.y; v[j8 * 8 + 2] += a.z; v[j8 * 8 + 3] += a.w;
+      v[j8 * 8 + 4] += b.x; v[j8 * 8 + 5] += b.y; v[j8 * 8 + 6] += b.z; v[j8 * 8 + 7] += b.w;
     }
-    __nv_bfloat162 h[4];
+  }
+}
+__device__ __forceinline__ void ln_affine32(float (&v)[32], float mean, float rstd, const float* __restrict__ gamma,
+                                            const float* __restrict__ beta) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>((bf16*)g.out_act + orow * g.ldo2 + n) = *reinterpret_cast<uint4*>(h);
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + j4 * 4));
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + j4 * 4));
+    v[j4 * 4 + 0] = fmaf((v[j4 * 4 + 0] - mean) * rstd, gm.x, bt.x);
+    v[j4 * 4 + 1] = fmaf((v[j4 * 4 + 1] - mean) * rstd, gm.y, bt.y);
+    v[j4 * 4 + 2] = fmaf((v[j4 * 4 + 2] - mean) * rstd, gm.z, bt.z);
+    v[j4 * 4 + 3] = fmaf((v[j4 * 4 + 3] - mean) * rstd, gm.w, bt.w);
+  }
+}
+__device__ __forceinline__ void act32(float (&v)[32], int act, float prm, const float* __restrict__ vec, int n_valid) {
+  switch (act) {
+    case ACT_GELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + fast_erf(v[j] * 0.70710678118654752440f));
+      break;
+    case ACT_ELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : __expf(v[j]) - 1.0f;
+      break;
+    case ACT_LRELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * prm;
+      break;
+    case ACT_MISH:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fast_mish(v[j]);
+      break;
+    case ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+      break;
+    case ACT_SNAKE:
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        if (j8 * 8 + 8 <= n_valid) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(vec + j8 * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(vec + j8 * 8 + 4));
+          const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float sn = __sinf(v[j8 * 8 + j] * al[j]);
+            v[j8 * 8 + j] = fmaf(__frcp_rn(al[j] + 1e-9f) * sn, sn, v[j8 * 8 + j]);
+          }
+        }
+      }
+      break;
+    default:
+      break;
+  }
+}
+__device__ __forceinline__ void acc_to_f32(const uint32_t (&acc)[32], float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+}
+
+struct TcMaps {
+  CUtensorMap a0, a1, w;        // operands (bf16, box 64 x rows, SWIZZLE_128B)
+  CUtensorMap resid;            // fp32 [view rows, N], box 32 x 32, SWIZZLE_128B
+  CUtensorMap out_f32;          // fp32 [view rows, N], box 32 x 32, SWIZZLE_128B
+  CUtensorMap out_act;          // bf16 [view rows, N], box 32 x 32, SWIZZLE_64B
+  CUtensorMap out_ln;           // bf16 [view rows, N], box 32 x 32, SWIZZLE_64B
+};
+
+struct TcParams {
+  int block_n, n_tiles_n, num_tiles, stages, b_stage_bytes;
+};
+
+// byte offset of 16-byte chunk j of row r inside a staging buffer
+__device__ __forceinline__ uint32_t swz128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint32_t swz64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Stage a 32x32 bf16 block held as one row per lane and TMA-store it.
+__device__ __forceinline__ void stage_store_b16(const CUtensorMap* tm, uint32_t hbuf, int lane, const float (&v)[32], int col, int row0) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    sts128u(hbuf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tm, hbuf, col, row0);
+    bulk_commit();
   }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_taps_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                    const __grid_constant__ CUtensorMap tmW, const GemmDesc g, const int block_n,
-                    const int n_tiles_n, const int num_tiles) {
+gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t smem_a = base;
-  const uint32_t smem_b = base + STAGES * A_STAGE_BYTES;
-  const uint32_t bars = smem_b + STAGES * B_STAGE_BYTES;
-  const uint32_t full_bar = bars;                      // STAGES x 8 B
-  const uint32_t empty_bar = bars + 8 * STAGES;        // STAGES x 8 B
-  const uint32_t tfull_bar = bars + 16 * STAGES;       // 2 x 8 B
-  const uint32_t tempty_bar = bars + 16 * STAGES + 16; // 2 x 8 B
-  const uint32_t tmem_slot = bars + 16 * STAGES + 32;  // 4 B
+  const uint32_t smem_b = smem_a + p.stages * A_STAGE_BYTES;
+  const uint32_t smem_epi = smem_b + p.stages * p.b_stage_bytes;  // EPI_WARPS x (4 KB + 2 KB), 1024-aligned pieces
+  const uint32_t bars = smem_epi + EPI_WARPS * EPI_BYTES_PER_WARP;
+  const uint32_t full_bar = bars;                        // MAX_STAGES x 8 B
+  const uint32_t empty_bar = bars + 8 * MAX_STAGES;      // MAX_STAGES x 8 B
+  const uint32_t tfull_bar = bars + 16 * MAX_STAGES;     // 2 x 8 B
+  const uint32_t tempty_bar = tfull_bar + 16;            // 2 x 8 B
+  const uint32_t epi_bar = tempty_bar + 16;              // EPI_WARPS x 8 B
+  const uint32_t tmem_slot = epi_bar + 8 * EPI_WARPS;    // 4 B
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,12 +319,12 @@ gemm_taps_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int k_iters = g.n_taps * k_blocks_per_tap;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA0) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA1) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.w) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < p.stages; ++i) {
       mbar_init(full_bar + 8 * i, 1);
       mbar_init(empty_bar + 8 * i, 1);
     }
@@ -186,6 +332,7 @@ gemm_taps_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       mbar_init(tfull_bar + 8 * i, 1);
       mbar_init(tempty_bar + 8 * i, 128);
     }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(epi_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -202,19 +349,19 @@ gemm_taps_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = A_STAGE_BYTES + block_n * BLOCK_K * 2;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles_n) * BLOCK_M;
-        const int n0 = (tile % n_tiles_n) * block_n;
+      const uint32_t tx_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles_n) * BLOCK_M;
+        const int n0 = (tile % p.n_tiles_n) * p.block_n;
         for (int s = 0; s < g.n_taps; ++s) {
-          const CUtensorMap* tmA = g.tap_src[s] ? &tmA1 : &tmA0;
+          const CUtensorMap* tmA = g.tap_src[s] ? &tm.a1 : &tm.a0;
           const int arow = m0 + g.tap_shift[s];
           for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
             mbar_expect_tx(full_bar + 8 * stage, tx_bytes);
             tma_load_2d(tmA, full_bar + 8 * stage, smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, arow);
-            tma_load_2d(&tmW, full_bar + 8 * stage, smem_b + stage * B_STAGE_BYTES, s * g.K_tap + kb * BLOCK_K, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            tma_load_2d(&tm.w, full_bar + 8 * stage, smem_b + stage * p.b_stage_bytes, s * g.K_tap + kb * BLOCK_K, n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -224,12 +371,12 @@ gemm_taps_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
       // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_stage * 256;
@@ -237,49 +384,172 @@ gemm_taps_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           mbar_wait(full_bar + 8 * stage, phase, 3);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_a + stage * A_STAGE_BYTES);
-          const uint64_t bdesc = make_smem_desc(smem_b + stage * B_STAGE_BYTES);
+          const uint64_t bdesc = make_smem_desc(smem_b + stage * p.b_stage_bytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 B (= 16 bf16) inside the 128 B swizzle row: +2 in the >>4 address field
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar + 8 * acc_stage);  // accumulator complete -> epilogue
         if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    int acc_stage = 0;
+    // ===================== epilogue: group = accumulator stage =====================
+    const int e = warp - 4;
+    const int q = e & 3;        // TMEM lane quarter (warp index % 4)
+    const int grp = e >> 2;     // accumulator stage served by this warp
+    const uint32_t fbuf = smem_epi + e * EPI_F32_BYTES;
+    const uint32_t hbuf = smem_epi + EPI_WARPS * EPI_F32_BYTES + e * EPI_B16_BYTES;
+    const uint32_t ebar = epi_bar + 8 * e;
+    uint32_t ephase = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles_n) * BLOCK_M;
-      const int n0 = (tile % n_tiles_n) * block_n;
-      mbar_wait(tfull_bar + 8 * acc_stage, acc_phase, 4);
+    const int n_chunks = p.block_n >> 5;
+    const bool has_f32_in = g.resid != nullptr;
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local_tile) {
+      if ((local_tile & 1) != grp) continue;
+      const int m0 = (tile / p.n_tiles_n) * BLOCK_M;
+      const int n0 = (tile % p.n_tiles_n) * p.block_n;
+      const int row0 = m0 + q * 32;  // first row (view coordinates) of this warp's 32-row slab
+      mbar_wait(tfull_bar + 8 * grp, acc_phase, 4);
+      acc_phase ^= 1;
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
+      const int m = row0 + lane;
       const long orow = (long)m * g.o_stride + g.o_off;
       const bool in_range = m < g.M && orow < g.o_rows;
-      const bool row_valid = in_range && (g.frame_row == nullptr || g.frame_row[orow] >= 0);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_stage * 256;
-      for (int c0 = 0; c0 < block_n; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + c0, acc);  // warp-collective: every lane participates
-        if (in_range) {
+      const int fr = (in_range && g.frame_row) ? g.frame_row[orow] : (in_range ? 0 : -1);
+      const bool row_valid = fr >= 0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256;
+      const float* add_row = (g.add_row && row_valid) ? g.add_row + (long)g.row_tidx[fr] * g.add_row_stride : nullptr;
+
+      // ---- optional pre-LayerNorm statistics of (acc + bias) over the whole row (block_n == N == 256)
+      float mean1 = 0.f, rstd1 = 1.f;
+      if (g.ln1_gamma) {
+        float s = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          float v[32];
+          acc_to_f32(acc, v);
+          if (g.bias) add_vec32(v, g.bias + n0 + c * 32, 32);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int n = n0 + c0 + j;
-            if (n + 8 <= g.N) epilogue8(g, orow, n, row_valid, acc + j);
+          for (int j = 0; j < 32; ++j) s += v[j];
+        }
+        mean1 = s * (1.0f / (float)g.N);
+        float qs = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          float v[32];
+          acc_to_f32(acc, v);
+          if (g.bias) add_vec32(v, g.bias + n0 + c * 32, 32);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = v[j] - mean1;
+            qs = fmaf(d, d, qs);
           }
+        }
+        rstd1 = rsqrtf(qs * (1.0f / (float)g.N) + 1e-5f);
+      }
+
+      // ---- main pass
+      float sum2 = 0.f;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= g.N) break;
+        const int n_valid = g.N - n < 32 ? g.N - n : 32;
+        if (lane == 0) {
+          bulk_wait_read0();  // staging buffers free again (previous TMA stores have read them)
+          if (has_f32_in) {
+            mbar_expect_tx(ebar, EPI_F32_BYTES);
+            tma_load_2d(&tm.resid, ebar, fbuf, n, row0);
+          }
+        }
+        uint32_t acc[32];
+        tmem_ld32(taddr + c * 32, acc);
+        float v[32];
+        acc_to_f32(acc, v);
+        if (g.bias) add_vec32(v, g.bias + n, n_valid);
+        if (g.ln1_gamma) ln_affine32(v, mean1, rstd1, g.ln1_gamma + n, g.ln1_beta + n);
+        if (g.act != ACT_NONE) act32(v, g.act, g.act_param, g.act_vec ? g.act_vec + n : nullptr, n_valid);
+        if (add_row) add_vec32(v, add_row + n, n_valid);
+        if (!row_valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        __syncwarp();  // lane 0's wait_group.read precedes every lane's staging writes
+        if (has_f32_in) {
+          mbar_wait(ebar, ephase, 5);
+          ephase ^= 1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r = lds128(fbuf + swz128(lane, j));
+            v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+          }
+        }
+        if (g.out_f32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128(fbuf + swz128(lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (g.ln2_gamma) {  // keep the final value in TMEM for the post-LayerNorm sweeps
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { acc[j] = __float_as_uint(v[j]); sum2 += v[j]; }
+          tmem_st32(taddr + c * 32, acc);
+        }
+        if (g.out_act) {
+          if (g.act2 != ACT_NONE) act32(v, g.act2, g.act2_param, g.act2_vec ? g.act2_vec + n : nullptr, n_valid);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128u(hbuf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (g.out_f32) tma_store_2d(&tm.out_f32, fbuf, n, row0);
+          if (g.out_act) tma_store_2d(&tm.out_act, hbuf, n, row0);
+          bulk_commit();
+        }
+      }
+
+      // ---- optional post-LayerNorm of the final value (norm1 / norm3 of the next transformer block)
+      if (g.ln2_gamma) {
+        const float mean2 = sum2 * (1.0f / (float)g.N);
+        float qs = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(acc[j]) - mean2;
+            qs = fmaf(d, d, qs);
+          }
+        }
+        const float rstd2 = rsqrtf(qs * (1.0f / (float)g.N) + 1e-5f);
+        for (int c = 0; c < n_chunks; ++c) {
+          const int n = n0 + c * 32;
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          float v[32];
+          acc_to_f32(acc, v);
+          ln_affine32(v, mean2, rstd2, g.ln2_gamma + n, g.ln2_beta + n);
+          if (!row_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          stage_store_b16(&tm.out_ln, hbuf, lane, v, n, row0);
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar + 8 * acc_stage);
-      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+      mbar_arrive(tempty_bar + 8 * grp);
     }
+    if (lane == 0) bulk_wait0();  // smem must outlive the last TMA store's reads
   }
 
   tc_fence_before();
@@ -301,24 +571,25 @@ PFN_encodeTiled get_encode_tiled();
 
 struct TmapKey {
   const void* ptr;
-  long inner, rows, pitch;
-  int box_rows;
+  long inner, rows, pitch_bytes;
+  int box_inner, box_rows, kind;  // kind: 0 = bf16 SW128 (operand), 1 = f32 SW128, 2 = bf16 SW64
   bool operator<(const TmapKey& o) const {
     if (ptr != o.ptr) return ptr < o.ptr;
     if (inner != o.inner) return inner < o.inner;
     if (rows != o.rows) return rows < o.rows;
-    if (pitch != o.pitch) return pitch < o.pitch;
-    return box_rows < o.box_rows;
+    if (pitch_bytes != o.pitch_bytes) return pitch_bytes < o.pitch_bytes;
+    if (box_inner != o.box_inner) return box_inner < o.box_inner;
+    if (box_rows != o.box_rows) return box_rows < o.box_rows;
+    return kind < o.kind;
   }
 };
 
 // Cache of encoded tensor maps (encoding costs ~1 us; the same buffers recur every layer / step).
 struct TmapCache {
   std::map<TmapKey, CUtensorMap> maps;
-  const CUtensorMap& get(const void* ptr, long inner_elems, long rows, long pitch_elems, int box_rows);
+  const CUtensorMap& get(const void* ptr, long inner_elems, long rows, long pitch_bytes, int box_inner, int box_rows, int kind);
 };
 
-// True when the tcgen05 kernel can run this problem (else the caller uses the FFMA engine).
 struct ProfileState {
   bool on = false;
   std::vector<cudaEvent_t> ev;  // pairs
@@ -326,6 +597,7 @@ struct ProfileState {
 };
 ProfileState& profile_state();
 
+// True when the tcgen05 kernel can run this problem (else the caller uses the FFMA engine).
 bool gemm_tc_supported(const GemmDesc& g);
 void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream_t st);
 

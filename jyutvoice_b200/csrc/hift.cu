@@ -206,7 +206,8 @@ struct HiftBuffers {
   double* D;                     // source phase prefix [B, 9, Tmax]
   void* SST;                     // [rows2, 18]
   void* P[4];                    // conv inputs per level: [Tm,512] [8Tm,256] [40Tm,128] [120Tm,64]
-  float *X[3], *S[3], *XS[3];    // per stage fp32 streams
+  float* X[3];                   // per stage: x after ups + source fusion (fp32)
+  float* S[3][3];                // per stage: the three ResBlock streams (S[i][0] first carries the source branch)
   void *XT[3], *XT2[3];          // per stage activation-typed conv inputs
   float* SPEC;                   // [rows2, 32]
 };
@@ -227,8 +228,7 @@ static HiftBuffers hift_carve(Arena& ar, const Engine& eng, const HiftLayout& L,
   for (int i = 0; i < 3; ++i) {
     const size_t n = (size_t)L.rows_alloc[i + 1] * STAGE_C[i];
     b.X[i] = ar.alloc<float>(n);
-    b.S[i] = ar.alloc<float>(n);
-    b.XS[i] = ar.alloc<float>(n);
+    for (int j = 0; j < 3; ++j) b.S[i][j] = ar.alloc<float>(n);
     b.XT[i] = ar.alloc<char>(n * es);
     b.XT2[i] = ar.alloc<char>(n * es);
   }
@@ -316,8 +316,7 @@ static void run_act_rows(const HCtx& c, const float* in, void* out, long n, int 
 // ResBlock (generator.py:90-97).  On entry XT holds Snake_{a1[0]}(x0).  The block's own stream lives in S.
 // Final value (x after the third pair) * final_scale goes to final_out (accumulating if asked) and,
 // optionally, act2(final_out) to final_act.
-static void run_resblock(const HCtx& c, const ResBlockW& w, int stage, const float* x0, float* S, void* XT, void* XT2, float* final_out,
-                         int final_accumulate, float final_scale, void* final_act, int final_act2, float final_act2_p) {
+static void run_resblock(const HCtx& c, const ResBlockW& w, int stage, const float* x0, float* S, void* XT, void* XT2) {
   Engine& e = c.h->eng;
   const int level = stage + 1;
   const int Cn = w.C;
@@ -332,24 +331,13 @@ static void run_resblock(const HCtx& c, const ResBlockW& w, int stage, const flo
     g = hconv_desc(c, w.c2[i], XT2, level, 1, (w.k - 1) / 2);
     g.resid = i == 0 ? x0 : S;
     g.ldr = Cn;
+    g.out_f32 = S;
+    g.ldo = Cn;
     if (i < 2) {
-      g.out_f32 = S;
-      g.ldo = Cn;
       g.out_act = XT;
       g.ldo2 = Cn;
       g.act2 = ACT_SNAKE;
       g.act2_vec = w.a1[i + 1];
-    } else {
-      g.out_f32 = final_out;
-      g.ldo = Cn;
-      g.accumulate = final_accumulate;
-      g.out_scale = final_scale;
-      if (final_act) {
-        g.out_act = final_act;
-        g.ldo2 = Cn;
-        g.act2 = final_act2;
-        g.act2_param = final_act2_p;
-      }
     }
     e.gemm(g, c.st);
   }
@@ -418,37 +406,7 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
     const UpW& U = h->ups[i];
     const int lv_in = i, lv_out = i + 1;
     const int Cn = STAGE_C[i];
-    // x = ups[i](leaky_relu(x)): one GEMM per output phase
-    for (int ph = 0; ph < U.u; ++ph) {
-      const UpPhase& P = U.phases[ph];
-      GemmDesc g = gemm_desc_default();
-      g.A[0] = c.b.P[i];
-      g.lda[0] = U.cin;
-      g.a_rows[0] = c.L.rows_alloc[lv_in];
-      g.n_taps = P.w.n_taps;
-      g.K_tap = U.cin;
-      for (int t = 0; t < P.w.n_taps; ++t) {
-        g.tap_src[t] = 0;
-        g.tap_shift[t] = P.shifts[t];
-      }
-      g.W = P.w.W;
-      g.M = c.L.rows[lv_in];
-      g.N = Cn;
-      g.bias = P.w.bias;
-      g.frame_row = c.b.fr[lv_out];
-      g.out_f32 = c.b.X[i];
-      g.ldo = Cn;
-      g.o_stride = U.u;
-      g.o_off = ph + (i == 2 ? 1 : 0);  // stage 2: ReflectionPad1d((1,0)) shifts the signal by one
-      g.o_rows = c.L.rows_alloc[lv_out];
-      g.algo_flops = 2.0 * (double)c.valid_rows[lv_in] * Cn * P.w.n_taps * U.cin;
-      e.gemm(g, c.st);
-    }
-    if (i == 2) {
-      hift_reflect_fix_kernel<<<cdiv(c.L.B * Cn, 128), 128, 0, c.st>>>(c.b.X[i], Cn, c.sq, STAGE_RATE[i]);
-      JV_LAUNCHED();
-    }
-    // si = source_resblocks[i](source_downs[i](s_stft)); x = x + si
+    // si = source_resblocks[i](source_downs[i](s_stft)) -> S[i][0]   (generator.py:411-412; independent of x)
     {
       const int su = SRC_U[i];
       const PackedW& w = h->src_down[i];
@@ -468,7 +426,7 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
       g.N = Cn;
       g.bias = w.bias;
       g.frame_row = c.b.fr[lv_out];
-      g.out_f32 = c.b.S[i];
+      g.out_f32 = c.b.S[i][0];
       g.ldo = Cn;
       g.out_act = c.b.XT[i];
       g.ldo2 = Cn;
@@ -476,16 +434,53 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
       g.act2_vec = h->src_rb[i].a1[0];
       g.o_rows = c.L.rows_alloc[lv_out];
       e.gemm(g, c.st);
-      run_resblock(c, h->src_rb[i], i, c.b.S[i], c.b.S[i], c.b.XT[i], c.b.XT2[i], c.b.X[i], 1, 1.0f, nullptr, ACT_NONE, 0.f);
+      run_resblock(c, h->src_rb[i], i, c.b.S[i][0], c.b.S[i][0], c.b.XT[i], c.b.XT2[i]);
+    }
+    // x = ups[i](leaky_relu(x)) + si: one GEMM per output phase, si added as the epilogue residual
+    for (int ph = 0; ph < U.u; ++ph) {
+      const UpPhase& P = U.phases[ph];
+      GemmDesc g = gemm_desc_default();
+      g.A[0] = c.b.P[i];
+      g.lda[0] = U.cin;
+      g.a_rows[0] = c.L.rows_alloc[lv_in];
+      g.n_taps = P.w.n_taps;
+      g.K_tap = U.cin;
+      for (int t = 0; t < P.w.n_taps; ++t) {
+        g.tap_src[t] = 0;
+        g.tap_shift[t] = P.shifts[t];
+      }
+      g.W = P.w.W;
+      g.M = c.L.rows[lv_in];
+      g.N = Cn;
+      g.bias = P.w.bias;
+      g.frame_row = c.b.fr[lv_out];
+      g.resid = c.b.S[i][0];
+      g.ldr = Cn;
+      g.out_f32 = c.b.X[i];
+      g.ldo = Cn;
+      g.o_stride = U.u;
+      g.o_off = ph + (i == 2 ? 1 : 0);  // stage 2: ReflectionPad1d((1,0)) shifts the signal by one
+      g.o_rows = c.L.rows_alloc[lv_out];
+      g.algo_flops = 2.0 * (double)c.valid_rows[lv_in] * Cn * P.w.n_taps * U.cin;
+      e.gemm(g, c.st);
+    }
+    if (i == 2) {
+      hift_reflect_fix_kernel<<<cdiv(c.L.B * Cn, 128), 128, 0, c.st>>>(c.b.X[i], c.b.S[i][0], Cn, c.sq, STAGE_RATE[i]);
+      JV_LAUNCHED();
     }
     // x = mean_j resblocks[3i+j](x); then leaky_relu for the next consumer (0.1 before ups, 0.01 before conv_post)
     const long n = (long)c.L.rows_alloc[lv_out] * Cn;
     for (int j = 0; j < 3; ++j) {
       const ResBlockW& w = h->rb[3 * i + j];
       run_act_rows(c, c.b.X[i], c.b.XT[i], n, Cn, ACT_SNAKE, 0.f, w.a1[0]);
-      run_resblock(c, w, i, c.b.X[i], c.b.S[i], c.b.XT[i], c.b.XT2[i], c.b.XS[i], j > 0 ? 1 : 0, 1.0f / 3.0f,
-                   j == 2 ? c.b.P[i + 1] : nullptr, ACT_LRELU, i == 2 ? 0.01f : 0.1f);
+      run_resblock(c, w, i, c.b.X[i], c.b.S[i][j], c.b.XT[i], c.b.XT2[i]);
     }
+    const float slope = i == 2 ? 0.01f : 0.1f;
+    if (e.is_bf16())
+      mean3_act_kernel<bf16><<<(unsigned)((n / 4 + 255) / 256), 256, 0, c.st>>>(c.b.S[i][0], c.b.S[i][1], c.b.S[i][2], (bf16*)c.b.P[i + 1], n, slope);
+    else
+      mean3_act_kernel<float><<<(unsigned)((n / 4 + 255) / 256), 256, 0, c.st>>>(c.b.S[i][0], c.b.S[i][1], c.b.S[i][2], (float*)c.b.P[i + 1], n, slope);
+    JV_LAUNCHED();
   }
   {
     GemmDesc g = hconv_desc(c, h->conv_post, c.b.P[3], 3, 1, 3);

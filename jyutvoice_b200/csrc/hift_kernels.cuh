@@ -167,13 +167,28 @@ __global__ void act_rows_kernel(const float* __restrict__ in, TA* __restrict__ o
   for (int j = 0; j < 4; ++j) out[i + j] = DT<TA>::from_f(r[j]);
 }
 
-// ReflectionPad1d((1,0)) at stage 2 (generator.py:407-408): position 0 := position 2 (= u[1])
-__global__ void hift_reflect_fix_kernel(float* __restrict__ X, int Cn, HiftSeq sq, int rate) {
+// ReflectionPad1d((1,0)) at stage 2 (generator.py:407-408): x[0] := u[1] (= position 2) before `x + si`.
+// X already holds u + si (si was the GEMM's residual), so position 0 = (X[2] - si[2]) + si[0].
+__global__ void hift_reflect_fix_kernel(float* __restrict__ X, const float* __restrict__ SI, int Cn, HiftSeq sq, int rate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= sq.B * Cn) return;
   int b = i / Cn, c = i % Cn;
   long r0 = (long)rate * sq.off[b];
-  X[r0 * Cn + c] = X[(r0 + 2) * Cn + c];
+  X[r0 * Cn + c] = (X[(r0 + 2) * Cn + c] - SI[(r0 + 2) * Cn + c]) + SI[r0 * Cn + c];
+}
+
+// x = (r0 + r1 + r2) / 3 (generator.py:415-421), then the leaky_relu of the next consumer -> conv input
+template <typename TA>
+__global__ void mean3_act_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                 TA* __restrict__ out, long n, float slope) {
+  long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float4 x = *reinterpret_cast<const float4*>(a + i);
+  const float4 y = *reinterpret_cast<const float4*>(b + i);
+  const float4 z = *reinterpret_cast<const float4*>(c + i);
+  float r[4] = {(x.x + y.x + z.x) / 3.0f, (x.y + y.y + z.y) / 3.0f, (x.z + y.z + z.z) / 3.0f, (x.w + y.w + z.w) / 3.0f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[i + j] = DT<TA>::from_f(r[j] > 0.f ? r[j] : r[j] * slope);
 }
 
 // ---------------------------------------------------------------- output head (generator.py:425-431, 383-394)

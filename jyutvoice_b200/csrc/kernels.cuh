@@ -78,13 +78,13 @@ __global__ void unpack_output_kernel(float* __restrict__ out, const float* __res
 // ------------------------------------------------------------------------------------------
 // LayerNorm over 256 channels of each frame (one warp per frame), optional Mish, optional per-row
 // vector add (time embedding), optional matrix add (res_conv branch), validity mask.
-//   y = LN(x) * g + b ; y = mish ? Mish(y) : y ; y += add_row[row_tidx[r] * add_row_stride + c] ; y = valid ? y : 0 ;
+//   y = LN(x) * g + b ; y = act(y) ; y += add_row[row_tidx[r] * add_row_stride + c] ; y = valid ? y : 0 ;
 //   y += add_mat[m, c] ; out_f32 / out_act
 // ------------------------------------------------------------------------------------------
 struct LnArgs {
   const float* x; int ldx;
   const float* gamma; const float* beta;
-  int mish;
+  int act;   // activation after the affine (ACT_MISH for CausalBlock1D, ACT_NONE for norm1 / norm3)
   const float* add_row; const int* row_tidx; int add_row_stride;
   const float* add_mat; int ld_add;
   const int* frame_row;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) ln256_kernel(const LnArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float y = (v[j] - mean) * rstd * __ldg(a.gamma + c0 + j) + __ldg(a.beta + c0 + j);
-    if (a.mish) y = act_mish(y);
+    y = apply_act(y, a.act, 0.f, 0.f);
     if (a.add_row && valid) y += a.add_row[(long)a.row_tidx[r] * a.add_row_stride + c0 + j];
     y = valid ? y : 0.f;
     if (a.add_mat) y += a.add_mat[(long)m * a.ld_add + c0 + j];
