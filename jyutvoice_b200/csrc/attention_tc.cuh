@@ -1,0 +1,238 @@
+// tcgen05 multi-head attention for the estimator's transformer blocks (bf16 mode).
+// 8 heads x 64, non-causal, keys masked by the row length (decoder.py:955-959: -1e10 bias on padded keys).
+// One CTA = 128 queries of one (row, head); keys are consumed in tiles of 128 with an online softmax:
+//   S = Q K^T      tcgen05.mma M=128 N=128 K=64      (Q, K tiles by TMA, 128B swizzle, K-major)
+//   P = softmax    one thread per query row: tcgen05.ld S, exp2, running max / sum, P -> smem (bf16, K-major)
+//   O += P V       tcgen05.mma M=128 N=64  K=128     (V tile by TMA is the MN-major B operand as it lies in memory)
+// O stays in TMEM across key tiles and is rescaled in place (tcgen05.ld / st) when the running max moves.
+// Two CTAs fit per SM (80 KB smem, 256 TMEM columns each), which overlaps one CTA's softmax with the other's MMAs.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace jv {
+namespace attn {
+
+constexpr int TQ = 128, TK = 128, HD = 64;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: one 128 x 64 bf16 tile
+constexpr int SMEM_BYTES = 1024 + 3 * TILE_BYTES + 2 * TILE_BYTES + 128;
+constexpr int THREADS = 160;
+constexpr int TMEM_COLS = 256;  // S: columns [0,128), O: columns [128,192)
+
+// MN-major SWIZZLE_128B descriptor for the V tile [keys][64 d]: rows of 128 B (64 d), 8-key groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 16;  // LBO: next 64-wide MN block (unused: N = 64 is one block)
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO: next group of 8 K rows (keys)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int ldo, const int* __restrict__ row_off,
+                    const int* __restrict__ row_len, float scale_log2e) {
+  using namespace tc;
+  const int r = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
+  const int len = row_len[r];
+  if (q0 >= len) return;
+  const int off = row_off[r];
+  const int nt = (len + TK - 1) / TK;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = base + 2 * TILE_BYTES, sP = base + 3 * TILE_BYTES;  // sP: 2 tiles
+  const uint32_t bars = sP + 2 * TILE_BYTES;
+  const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40;
+  const uint32_t tmem_slot = bars + 48;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(bar_q, 1);
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmQKV) : "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // instruction descriptors: bf16 x bf16 -> fp32, M = 128; S: N = 128 both K-major; PV: N = 64, B MN-major (bit 16)
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TK >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
+      mbar_expect_tx(bar_q, TILE_BYTES);
+      tma_load_2d(&tmQKV, bar_q, sQ, h * HD, off + q0);
+      mbar_expect_tx(bar_k, TILE_BYTES);
+      tma_load_2d(&tmQKV, bar_k, sK, 512 + h * HD, off);
+      mbar_expect_tx(bar_v, TILE_BYTES);
+      tma_load_2d(&tmQKV, bar_v, sV, 1024 + h * HD, off);
+      mbar_wait(bar_q, 0, 10);
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t ph = j & 1;
+        mbar_wait(bar_k, ph, 11);
+        tc_fence_after();
+        {
+          const uint64_t adesc = make_smem_desc(sQ), bdesc = make_smem_desc(sK);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, adesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_s);
+        }
+        if (j + 1 < nt) {  // K buffer is free once S has been computed
+          mbar_wait(bar_s, ph, 12);
+          mbar_expect_tx(bar_k, TILE_BYTES);
+          tma_load_2d(&tmQKV, bar_k, sK, 512 + h * HD, off + (j + 1) * TK);
+        }
+        mbar_wait(bar_p, ph, 13);
+        tc_fence_after();
+        mbar_wait(bar_v, ph, 14);
+        {
+#pragma unroll
+          for (int s = 0; s < TK / 16; ++s) {
+            // A = P: two K-major 128x64 tiles; step s covers keys [16 s, 16 s + 16)
+            const uint64_t adesc = make_smem_desc(sP + (s >> 2) * TILE_BYTES) + 2 * (s & 3);
+            const uint64_t bdesc = make_smem_desc_mn(sV + s * 2048);
+            umma_bf16(tO, adesc, bdesc, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_o);
+        }
+        if (j + 1 < nt) {  // V buffer (and P) free once O has been updated
+          mbar_wait(bar_o, ph, 15);
+          mbar_expect_tx(bar_v, TILE_BYTES);
+          tma_load_2d(&tmQKV, bar_v, sV, 1024 + h * HD, off + (j + 1) * TK);
+        }
+      }
+    }
+  } else {
+    // ===================== softmax: one thread per query row =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nt; ++j) {
+      const uint32_t ph = j & 1;
+      const int k0 = j * TK;
+      const int kvalid = len - k0 < TK ? len - k0 : TK;
+      mbar_wait(bar_s, ph, 16);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(tS + lane_addr + c * 32, acc);
+        if (c * 32 < kvalid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = (c * 32 + i < kvalid) ? __uint_as_float(acc[i]) : -INFINITY;
+            mx = fmaxf(mx, x);
+          }
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * scale_log2e);
+      const float alpha = fast_exp2(m_run - m_new);  // 0 at j == 0
+      if (j > 0) {
+        mbar_wait(bar_o, ph ^ 1, 17);  // O_{j-1} accumulated: O is stable and the P buffer is free
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + lane_addr + c * 32, o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tO + lane_addr + c * 32, o);
+        }
+      }
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(tS + lane_addr + c * 32, acc);
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float pr = (c * 32 + i < kvalid) ? fast_exp2(fmaf(__uint_as_float(acc[i]), scale_log2e, -m_new)) : 0.f;
+          pv[i] = pr;
+          lsum += pr;
+        }
+        // P[row][key]: K-major SWIZZLE_128B, tile = key / 64, 16-byte chunk = (key % 64) / 8
+        const uint32_t tile = sP + (c >> 1) * TILE_BYTES;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int chunk = (c & 1) * 4 + g8;
+          sts128u(tile + swz128(row, chunk), pack_bf16(pv[8 * g8], pv[8 * g8 + 1]), pack_bf16(pv[8 * g8 + 2], pv[8 * g8 + 3]),
+                  pack_bf16(pv[8 * g8 + 4], pv[8 * g8 + 5]), pack_bf16(pv[8 * g8 + 6], pv[8 * g8 + 7]));
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      fence_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_o, (nt - 1) & 1, 18);
+    tc_fence_after();
+    const int t = q0 + row;
+    const float inv = 1.0f / l_run;
+    bf16* dst = out + (long)(off + t) * ldo + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + lane_addr + c * 32, o);
+      if (t < len) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[8 * g8]) * inv, __uint_as_float(o[8 * g8 + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(o[8 * g8 + 2]) * inv, __uint_as_float(o[8 * g8 + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(o[8 * g8 + 4]) * inv, __uint_as_float(o[8 * g8 + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(o[8 * g8 + 6]) * inv, __uint_as_float(o[8 * g8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + g8 * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace attn
+
+static inline void launch_attention_tc(TmapCache& cache, const void* qkv, void* out, const int* row_off, const int* row_len,
+                                       long M_alloc, int R, int Tmax_len, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    JV_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
+    attr = true;
+  }
+  const CUtensorMap& tm = cache.get(qkv, 1536, M_alloc, 1536 * 2, 64, 128, 0);
+  dim3 grid(cdiv(Tmax_len, attn::TQ), 8, R);
+  attn::attention_tc_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tm, (bf16*)out, 512, row_off, row_len,
+                                                                          0.125f * 1.4426950408889634f);
+  JV_LAUNCHED();
+}
+
+}  // namespace jv

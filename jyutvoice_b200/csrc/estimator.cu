@@ -6,6 +6,7 @@
 
 #include "engine.cuh"
 #include "kernels.cuh"
+#include "attention_tc.cuh"
 #include "weights.cuh"
 
 namespace jv {
@@ -246,19 +247,18 @@ static GemmDesc conv_desc(const FwdCtx& c, const PackedW& w, const void* A0p, co
 }
 
 static void run_attention(const FwdCtx& c) {
+  if (c.h->eng.is_bf16()) {  // tcgen05 flash-style kernel
+    launch_attention_tc(c.h->eng.tmaps, c.b.QKV, c.b.ATT, c.b.row_off, c.b.row_len, c.M_alloc, c.R, c.Tmax_len, c.st);
+    return;
+  }
   static bool attr = false;
   if (!attr) {
     JV_CUDA(cudaFuncSetAttribute(attention_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    JV_CUDA(cudaFuncSetAttribute(attention_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     attr = true;
   }
   dim3 grid(cdiv(c.Tmax_len, 64), 8, c.R);
-  if (c.h->eng.is_bf16())
-    attention_simt_kernel<bf16><<<grid, 256, ATT_SMEM_BYTES, c.st>>>((const bf16*)c.b.QKV, 1536, (bf16*)c.b.ATT, 512, c.b.row_off,
-                                                                     c.b.row_len, 0.125f);
-  else
-    attention_simt_kernel<float><<<grid, 256, ATT_SMEM_BYTES, c.st>>>((const float*)c.b.QKV, 1536, (float*)c.b.ATT, 512,
-                                                                      c.b.row_off, c.b.row_len, 0.125f);
+  attention_simt_kernel<float><<<grid, 256, ATT_SMEM_BYTES, c.st>>>((const float*)c.b.QKV, 1536, (float*)c.b.ATT, 512, c.b.row_off,
+                                                                    c.b.row_len, 0.125f);
   JV_LAUNCHED();
 }
 

@@ -208,8 +208,17 @@ __device__ __forceinline__ void ln_affine32(float (&v)[32], float mean, float rs
 __device__ __forceinline__ void act32(float (&v)[32], int act, float prm, const float* __restrict__ vec, int n_valid) {
   switch (act) {
     case ACT_GELU:
+      // bf16 mode: GELU through the hardware tanh (tanh.approx.f32).  |GELU_tanh - GELU_erf| <= 4.7e-4, measured
+      // end effect on the estimator output 6e-4 max-abs vs 3e-2 from the bf16 operands.  fp32 mode uses erff.
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.f + fast_erf(v[j] * 0.70710678118654752440f));
+      for (int j = 0; j < 32; ++j) {
+        const float x = v[j];
+        const float u = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+        const float hx = 0.5f * x;
+        v[j] = fmaf(hx, th, hx);
+      }
       break;
     case ACT_ELU:
 #pragma unroll
@@ -428,19 +437,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 
       // ---- optional pre-LayerNorm statistics of (acc + bias) over the whole row (block_n == N == 256)
       float mean1 = 0.f, rstd1 = 1.f;
-      if (g.ln1_gamma) {
-        float s = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t acc[32];
-          tmem_ld32(taddr + c * 32, acc);
-          float v[32];
-          acc_to_f32(acc, v);
-          if (g.bias) add_vec32(v, g.bias + n0 + c * 32, 32);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s += v[j];
-        }
-        mean1 = s * (1.0f / (float)g.N);
-        float qs = 0.f;
+      if (g.ln1_gamma) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
+        float s1 = 0.f, s2 = 0.f;
         for (int c = 0; c < n_chunks; ++c) {
           uint32_t acc[32];
           tmem_ld32(taddr + c * 32, acc);
@@ -449,15 +447,16 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           if (g.bias) add_vec32(v, g.bias + n0 + c * 32, 32);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float d = v[j] - mean1;
-            qs = fmaf(d, d, qs);
+            s1 += v[j];
+            s2 = fmaf(v[j], v[j], s2);
           }
         }
-        rstd1 = rsqrtf(qs * (1.0f / (float)g.N) + 1e-5f);
+        mean1 = s1 * (1.0f / (float)g.N);
+        rstd1 = rsqrtf(fmaxf(s2 * (1.0f / (float)g.N) - mean1 * mean1, 0.f) + 1e-5f);
       }
 
       // ---- main pass
-      float sum2 = 0.f;
+      float sum2 = 0.f, sq2 = 0.f;
       for (int c = 0; c < n_chunks; ++c) {
         const int n = n0 + c * 32;
         if (n >= g.N) break;
@@ -497,7 +496,11 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         }
         if (g.ln2_gamma) {  // keep the final value in TMEM for the post-LayerNorm sweeps
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { acc[j] = __float_as_uint(v[j]); sum2 += v[j]; }
+          for (int j = 0; j < 32; ++j) {
+            acc[j] = __float_as_uint(v[j]);
+            sum2 += v[j];
+            sq2 = fmaf(v[j], v[j], sq2);
+          }
           tmem_st32(taddr + c * 32, acc);
         }
         if (g.out_act) {
@@ -519,17 +522,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       // ---- optional post-LayerNorm of the final value (norm1 / norm3 of the next transformer block)
       if (g.ln2_gamma) {
         const float mean2 = sum2 * (1.0f / (float)g.N);
-        float qs = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t acc[32];
-          tmem_ld32(taddr + c * 32, acc);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(acc[j]) - mean2;
-            qs = fmaf(d, d, qs);
-          }
-        }
-        const float rstd2 = rsqrtf(qs * (1.0f / (float)g.N) + 1e-5f);
+        const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / (float)g.N) - mean2 * mean2, 0.f) + 1e-5f);
         for (int c = 0; c < n_chunks; ++c) {
           const int n = n0 + c * 32;
           uint32_t acc[32];
