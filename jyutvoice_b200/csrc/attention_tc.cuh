@@ -88,36 +88,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       mbar_expect_tx(bar_v, TILE_BYTES);
       tma_load_2d(&tmQKV, bar_v, sV, 1024 + h * HD, off);
       mbar_wait(bar_q, 0, 10);
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T; afterwards the K buffer is reloaded with tile j + 1
+        mbar_wait(bar_k, j & 1, 11);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(sQ), bdesc = make_smem_desc(sK);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, adesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+      };
+      issue_s(0);
       for (int j = 0; j < nt; ++j) {
         const uint32_t ph = j & 1;
-        mbar_wait(bar_k, ph, 11);
-        tc_fence_after();
-        {
-          const uint64_t adesc = make_smem_desc(sQ), bdesc = make_smem_desc(sK);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16(tS, adesc + 2 * k, bdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(bar_s);
-        }
-        if (j + 1 < nt) {  // K buffer is free once S has been computed
+        if (j + 1 < nt) {  // K buffer is free once S_j has been computed
           mbar_wait(bar_s, ph, 12);
           mbar_expect_tx(bar_k, TILE_BYTES);
           tma_load_2d(&tmQKV, bar_k, sK, 512 + h * HD, off + (j + 1) * TK);
         }
-        mbar_wait(bar_p, ph, 13);
+        mbar_wait(bar_p, ph, 13);  // softmax j done: P_j in smem, O rescaled, S buffer free
         tc_fence_after();
         mbar_wait(bar_v, ph, 14);
-        {
 #pragma unroll
-          for (int s = 0; s < TK / 16; ++s) {
-            // A = P: two K-major 128x64 tiles; step s covers keys [16 s, 16 s + 16)
-            const uint64_t adesc = make_smem_desc(sP + (s >> 2) * TILE_BYTES) + 2 * (s & 3);
-            const uint64_t bdesc = make_smem_desc_mn(sV + s * 2048);
-            umma_bf16(tO, adesc, bdesc, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
-          }
-          umma_commit(bar_o);
+        for (int s = 0; s < TK / 16; ++s) {
+          // A = P: two K-major 128x64 tiles; step s covers keys [16 s, 16 s + 16)
+          const uint64_t adesc = make_smem_desc(sP + (s >> 2) * TILE_BYTES) + 2 * (s & 3);
+          const uint64_t bdesc = make_smem_desc_mn(sV + s * 2048);
+          umma_bf16(tO, adesc, bdesc, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
         }
-        if (j + 1 < nt) {  // V buffer (and P) free once O has been updated
-          mbar_wait(bar_o, ph, 15);
+        umma_commit(bar_o);
+        if (j + 1 < nt) {
+          issue_s(j + 1);  // queued right behind PV_j: the next softmax starts while O is still accumulating
+          mbar_wait(bar_o, ph, 15);  // V buffer (and P) free once O has been updated
           mbar_expect_tx(bar_v, TILE_BYTES);
           tma_load_2d(&tmQKV, bar_v, sV, 1024 + h * HD, off + (j + 1) * TK);
         }

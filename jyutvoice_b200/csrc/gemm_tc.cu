@@ -1,5 +1,7 @@
 // Host side of the tcgen05 GEMM: tensor-map encoding (driver entry point fetched at run time, so the
 // library does not link libcuda), tile-shape / pipeline-depth choice and launch.
+#include <stdlib.h>
+
 #include "gemm_tc.cuh"
 
 namespace jv {
@@ -41,6 +43,38 @@ ProfileState& profile_state() {
   return s;
 }
 
+// JYUTVOICE_B200_CLUSTER=0 disables the 2-CTA weight multicast (debugging aid)
+static bool use_cluster() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_CLUSTER");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+typedef void (*KernelFn)(const tc::TcMaps, const GemmDesc, const tc::TcParams);
+struct KernelEntry {
+  int epi;
+  KernelFn fn;
+};
+constexpr int N_KERNELS = 8;
+// the epilogue shapes the estimator / HiFT graphs actually use, plus the run-time generic kernel (last)
+static const KernelEntry* kernel_table() {
+  using namespace tc;
+  static const KernelEntry t[N_KERNELS] = {
+      {EPI_OACT, gemm_taps_tc_kernel<EPI_OACT>},                                              // QKV, FF1, plain convs
+      {EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_LN2>},    // out-proj, FF2 (+ next norm)
+      {EPI_RESID | EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_OACT>},  // last FF2 of a group, HiFT conv2
+      {EPI_LN1 | EPI_OACT, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT>},                          // CausalBlock1D (block1, final_block)
+      {EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>},  // block2 + res + norm1
+      {EPI_F32, gemm_taps_tc_kernel<EPI_F32>},                                                // res_conv, final_proj, conv_post
+      {EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_RESID | EPI_F32>},                        // HiFT ups + source, last conv2
+      {-1, gemm_taps_tc_kernel<-1>},
+  };
+  return t;
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 bool gemm_tc_supported(const GemmDesc& g) {
@@ -73,7 +107,8 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   if (g.M <= 0 || g.N <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
-    JV_CUDA(cudaFuncSetAttribute(tc::gemm_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+    for (int i = 0; i < N_KERNELS; ++i)
+      JV_CUDA(cudaFuncSetAttribute((const void*)kernel_table()[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
     attr_set = true;
   }
   tc::TcParams p;
@@ -92,12 +127,15 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   tc::TcMaps tm;
   tm.a0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], (long)g.lda[0] * 2, tc::BLOCK_K, tc::BLOCK_M, 0);
   tm.a1 = g.A[1] ? cache.get(g.A[1], g.K_tap, g.a_rows[1], (long)g.lda[1] * 2, tc::BLOCK_K, tc::BLOCK_M, 0) : tm.a0;
-  tm.w = cache.get(g.W, Ktot, g.N, Ktot * 2, tc::BLOCK_K, p.block_n, 0);
+  p.cluster = (m_tiles >= 2 && p.block_n % 16 == 0 && use_cluster()) ? 2 : 1;
+  p.num_units = cdiv(m_tiles, p.cluster) * p.n_tiles_n;
+  tm.w = cache.get(g.W, Ktot, g.N, Ktot * 2, tc::BLOCK_K, p.block_n / p.cluster, 0);
   tm.resid = g.resid ? out_view(cache, g, g.resid, g.ldr, 4, 1) : tm.a0;
   tm.out_f32 = g.out_f32 ? out_view(cache, g, g.out_f32, g.ldo, 4, 1) : tm.a0;
   tm.out_act = g.out_act ? out_view(cache, g, g.out_act, g.ldo2, 2, 2) : tm.a0;
   tm.out_ln = g.out_ln ? out_view(cache, g, g.out_ln, g.ldo3, 2, 2) : tm.a0;
-  const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  int grid = p.num_units * p.cluster < num_sms ? p.num_units * p.cluster : num_sms;
+  grid -= grid % p.cluster;
   ProfileState& ps = profile_state();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ps.on) {
@@ -105,7 +143,25 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
     JV_CUDA(cudaEventCreate(&e1));
     JV_CUDA(cudaEventRecord(e0, st));
   }
-  tc::gemm_taps_tc_kernel<<<grid, tc::NUM_THREADS, smem, st>>>(tm, g, p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int epi = (g.ln1_gamma ? tc::EPI_LN1 : 0) | (g.resid ? tc::EPI_RESID : 0) | (g.out_f32 ? tc::EPI_F32 : 0) |
+                  (g.out_act ? tc::EPI_OACT : 0) | (g.ln2_gamma ? tc::EPI_LN2 : 0);
+  KernelFn fn = kernel_table()[N_KERNELS - 1].fn;  // generic
+  for (int i = 0; i < N_KERNELS - 1; ++i)
+    if (kernel_table()[i].epi == epi) fn = kernel_table()[i].fn;
+  JV_CUDA(cudaLaunchKernelEx(&cfg, fn, tm, g, p));
   JV_LAUNCHED();
   if (ps.on) {
     JV_CUDA(cudaEventRecord(e1, st));

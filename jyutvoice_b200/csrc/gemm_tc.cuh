@@ -29,7 +29,7 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_F32_BYTES = 32 * 32 * 4;  // 4 KB: 32 rows x 128 B, SWIZZLE_128B
 constexpr int EPI_B16_BYTES = 32 * 32 * 2;  // 2 KB: 32 rows x 64 B, SWIZZLE_64B
-constexpr int EPI_BYTES_PER_WARP = EPI_F32_BYTES + EPI_B16_BYTES;
+constexpr int EPI_BYTES_PER_WARP = 2 * EPI_F32_BYTES;  // two 4 KB staging buffers per epilogue warp (double buffering)
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TMEM_COLS = 512;
@@ -80,6 +80,25 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar,
       ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)tm), "r"(src), "r"(c0), "r"(c1)
@@ -87,6 +106,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -270,6 +290,9 @@ struct TcMaps {
 
 struct TcParams {
   int block_n, n_tiles_n, num_tiles, stages, b_stage_bytes;
+  int cluster;    // CTAs per cluster (1 or 2): the CTAs of a cluster work on consecutive m-tiles of the same n-tile and
+                  // each loads 1/cluster of the weight tile, multicast to all of them (halves the L2 -> SM weight traffic)
+  int num_units;  // ceil(m_tiles / cluster) * n_tiles_n
 };
 
 // byte offset of 16-byte chunk j of row r inside a staging buffer
@@ -306,8 +329,18 @@ __device__ __forceinline__ void stage_store_b16(const CUtensorMap* tm, uint32_t 
   }
 }
 
+// EPI: compile-time epilogue feature mask (specialised instantiations keep the per-chunk instruction stream short);
+// EPI < 0 is the generic kernel that tests the descriptor at run time.
+constexpr int EPI_LN1 = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_OACT = 8, EPI_LN2 = 16;
+
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const TcParams p) {
+  const bool F_LN1 = EPI >= 0 ? (EPI & EPI_LN1) != 0 : g.ln1_gamma != nullptr;
+  const bool F_RESID = EPI >= 0 ? (EPI & EPI_RESID) != 0 : g.resid != nullptr;
+  const bool F_F32 = EPI >= 0 ? (EPI & EPI_F32) != 0 : g.out_f32 != nullptr;
+  const bool F_OACT = EPI >= 0 ? (EPI & EPI_OACT) != 0 : g.out_act != nullptr;
+  const bool F_LN2 = EPI >= 0 ? (EPI & EPI_LN2) != 0 : g.ln2_gamma != nullptr;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -319,13 +352,17 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const uint32_t empty_bar = bars + 8 * MAX_STAGES;      // MAX_STAGES x 8 B
   const uint32_t tfull_bar = bars + 16 * MAX_STAGES;     // 2 x 8 B
   const uint32_t tempty_bar = tfull_bar + 16;            // 2 x 8 B
-  const uint32_t epi_bar = tempty_bar + 16;              // EPI_WARPS x 8 B
-  const uint32_t tmem_slot = epi_bar + 8 * EPI_WARPS;    // 4 B
+  const uint32_t epi_bar = tempty_bar + 16;              // EPI_WARPS x 2 x 8 B (one per staging buffer)
+  const uint32_t tmem_slot = epi_bar + 16 * EPI_WARPS;   // 4 B
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_blocks_per_tap = g.K_tap / BLOCK_K;
   const int k_iters = g.n_taps * k_blocks_per_tap;
+  const int csz = p.cluster;
+  const int cta_rank = csz > 1 ? (int)cluster_cta_rank() : 0;
+  const int unit0 = blockIdx.x / csz, unit_step = gridDim.x / csz;
+  const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a0) : "memory");
@@ -335,13 +372,13 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(full_bar + 8 * i, 1);
-      mbar_init(empty_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, csz);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
       mbar_init(tempty_bar + 8 * i, 128);
     }
-    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(epi_bar + 8 * i, 1);
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(epi_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -350,6 +387,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   }
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -359,9 +397,10 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles_n) * BLOCK_M;
-        const int n0 = (tile % p.n_tiles_n) * p.block_n;
+      const int b_rows = p.block_n / csz;  // weight rows this CTA fetches (and multicasts)
+      for (int unit = unit0; unit < p.num_units; unit += unit_step) {
+        const int m0 = ((unit / p.n_tiles_n) * csz + cta_rank) * BLOCK_M;
+        const int n0 = (unit % p.n_tiles_n) * p.block_n;
         for (int s = 0; s < g.n_taps; ++s) {
           const CUtensorMap* tmA = g.tap_src[s] ? &tm.a1 : &tm.a0;
           const int arow = m0 + g.tap_shift[s];
@@ -369,7 +408,11 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
             mbar_expect_tx(full_bar + 8 * stage, tx_bytes);
             tma_load_2d(tmA, full_bar + 8 * stage, smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, arow);
-            tma_load_2d(&tm.w, full_bar + 8 * stage, smem_b + stage * p.b_stage_bytes, s * g.K_tap + kb * BLOCK_K, n0);
+            if (csz == 1)
+              tma_load_2d(&tm.w, full_bar + 8 * stage, smem_b + stage * p.b_stage_bytes, s * g.K_tap + kb * BLOCK_K, n0);
+            else
+              tma_load_2d_mcast(&tm.w, full_bar + 8 * stage, smem_b + stage * p.b_stage_bytes + cta_rank * b_rows * BLOCK_K * 2,
+                                s * g.K_tap + kb * BLOCK_K, n0 + cta_rank * b_rows, cmask);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -385,7 +428,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_stage * 256;
@@ -399,7 +442,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             // advance 32 B (= 16 bf16) inside the 128 B swizzle row: +2 in the >>4 address field
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in every CTA of the cluster: the peers multicast into it) when these MMAs retire
+          if (csz == 1) umma_commit(empty_bar + 8 * stage);
+          else umma_commit_mcast(empty_bar + 8 * stage, cmask);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar + 8 * acc_stage);  // accumulator complete -> epilogue
@@ -411,18 +456,21 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     const int e = warp - 4;
     const int q = e & 3;        // TMEM lane quarter (warp index % 4)
     const int grp = e >> 2;     // accumulator stage served by this warp
-    const uint32_t fbuf = smem_epi + e * EPI_F32_BYTES;
-    const uint32_t hbuf = smem_epi + EPI_WARPS * EPI_F32_BYTES + e * EPI_B16_BYTES;
-    const uint32_t ebar = epi_bar + 8 * e;
-    uint32_t ephase = 0;
+    // Two 4 KB staging buffers.  Normal mode: chunk c lives entirely in buffer c & 1 (residual in, fp32 or bf16
+    // out), so the TMA load of chunk c + 1 and the TMA store of chunk c - 1 overlap the math of chunk c.
+    // Dual-output mode (fp32 traffic AND a bf16 copy): buffer 0 = fp32, buffer 1 = bf16, no overlap.
+    const uint32_t sbuf0 = smem_epi + e * EPI_BYTES_PER_WARP;
+    const uint32_t ebar0 = epi_bar + 16 * e;
+    uint32_t ephase = 0;  // bit b = phase parity of staging buffer b's mbarrier
+    const bool dual = (F_RESID || F_F32) && F_OACT;
     uint32_t acc_phase = 0;
     const int n_chunks = p.block_n >> 5;
-    const bool has_f32_in = g.resid != nullptr;
+    const bool has_f32_in = F_RESID;
     int local_tile = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local_tile) {
+    for (int unit = unit0; unit < p.num_units; unit += unit_step, ++local_tile) {
       if ((local_tile & 1) != grp) continue;
-      const int m0 = (tile / p.n_tiles_n) * BLOCK_M;
-      const int n0 = (tile % p.n_tiles_n) * p.block_n;
+      const int m0 = ((unit / p.n_tiles_n) * csz + cta_rank) * BLOCK_M;
+      const int n0 = (unit % p.n_tiles_n) * p.block_n;
       const int row0 = m0 + q * 32;  // first row (view coordinates) of this warp's 32-row slab
       mbar_wait(tfull_bar + 8 * grp, acc_phase, 4);
       acc_phase ^= 1;
@@ -433,11 +481,11 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const int fr = (in_range && g.frame_row) ? g.frame_row[orow] : (in_range ? 0 : -1);
       const bool row_valid = fr >= 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256;
-      const float* add_row = (g.add_row && row_valid) ? g.add_row + (long)g.row_tidx[fr] * g.add_row_stride : nullptr;
+      const float* add_row = (F_LN1 && g.add_row && row_valid) ? g.add_row + (long)g.row_tidx[fr] * g.add_row_stride : nullptr;
 
       // ---- optional pre-LayerNorm statistics of (acc + bias) over the whole row (block_n == N == 256)
       float mean1 = 0.f, rstd1 = 1.f;
-      if (g.ln1_gamma) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
+      if (F_LN1) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
         float s1 = 0.f, s2 = 0.f;
         for (int c = 0; c < n_chunks; ++c) {
           uint32_t acc[32];
@@ -457,15 +505,29 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 
       // ---- main pass
       float sum2 = 0.f, sq2 = 0.f;
-      for (int c = 0; c < n_chunks; ++c) {
+      const int n_chunks_valid = (g.N - n0 + 31) / 32 < n_chunks ? (g.N - n0 + 31) / 32 : n_chunks;
+      if (has_f32_in && lane == 0) {  // residual of the first chunk
+        bulk_wait_read0();
+        mbar_expect_tx(ebar0, EPI_F32_BYTES);
+        tma_load_2d(&tm.resid, ebar0, sbuf0, n0, row0);
+      }
+      for (int c = 0; c < n_chunks_valid; ++c) {
         const int n = n0 + c * 32;
-        if (n >= g.N) break;
         const int n_valid = g.N - n < 32 ? g.N - n : 32;
+        const int bi = dual ? 0 : (c & 1);
+        const uint32_t fbuf = sbuf0 + bi * EPI_F32_BYTES;
+        const uint32_t hbuf = dual ? sbuf0 + EPI_F32_BYTES : fbuf;
         if (lane == 0) {
-          bulk_wait_read0();  // staging buffers free again (previous TMA stores have read them)
           if (has_f32_in) {
-            mbar_expect_tx(ebar, EPI_F32_BYTES);
-            tma_load_2d(&tm.resid, ebar, fbuf, n, row0);
+            if (!dual && c + 1 < n_chunks_valid) {  // prefetch the next chunk's residual into the other buffer
+              bulk_wait_read0();                    // ... once the store of chunk c - 1 has left it
+              mbar_expect_tx(ebar0 + 8 * (bi ^ 1), EPI_F32_BYTES);
+              tma_load_2d(&tm.resid, ebar0 + 8 * (bi ^ 1), sbuf0 + (bi ^ 1) * EPI_F32_BYTES, n + 32, row0);
+            }
+          } else if (dual) {
+            bulk_wait_read0();
+          } else {
+            bulk_wait_read1();  // the store of chunk c - 2 used this buffer
           }
         }
         uint32_t acc[32];
@@ -473,7 +535,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         float v[32];
         acc_to_f32(acc, v);
         if (g.bias) add_vec32(v, g.bias + n, n_valid);
-        if (g.ln1_gamma) ln_affine32(v, mean1, rstd1, g.ln1_gamma + n, g.ln1_beta + n);
+        if (F_LN1) ln_affine32(v, mean1, rstd1, g.ln1_gamma + n, g.ln1_beta + n);
         if (g.act != ACT_NONE) act32(v, g.act, g.act_param, g.act_vec ? g.act_vec + n : nullptr, n_valid);
         if (add_row) add_vec32(v, add_row + n, n_valid);
         if (!row_valid) {
@@ -482,19 +544,19 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         }
         __syncwarp();  // lane 0's wait_group.read precedes every lane's staging writes
         if (has_f32_in) {
-          mbar_wait(ebar, ephase, 5);
-          ephase ^= 1;
+          mbar_wait(ebar0 + 8 * bi, (ephase >> bi) & 1u, 5);
+          ephase ^= 1u << bi;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 r = lds128(fbuf + swz128(lane, j));
             v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
           }
         }
-        if (g.out_f32) {
+        if (F_F32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) sts128(fbuf + swz128(lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        if (g.ln2_gamma) {  // keep the final value in TMEM for the post-LayerNorm sweeps
+        if (F_LN2) {  // keep the final value in TMEM for the post-LayerNorm sweep
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             acc[j] = __float_as_uint(v[j]);
@@ -503,7 +565,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           }
           tmem_st32(taddr + c * 32, acc);
         }
-        if (g.out_act) {
+        if (F_OACT) {
           if (g.act2 != ACT_NONE) act32(v, g.act2, g.act2_param, g.act2_vec ? g.act2_vec + n : nullptr, n_valid);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -513,14 +575,19 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (g.out_f32) tma_store_2d(&tm.out_f32, fbuf, n, row0);
-          if (g.out_act) tma_store_2d(&tm.out_act, hbuf, n, row0);
+          if (F_F32) tma_store_2d(&tm.out_f32, fbuf, n, row0);
+          if (F_OACT) tma_store_2d(&tm.out_act, hbuf, n, row0);
           bulk_commit();
+          if (dual && has_f32_in && c + 1 < n_chunks_valid) {  // no second fp32 buffer in dual mode: load after the store
+            bulk_wait_read0();
+            mbar_expect_tx(ebar0, EPI_F32_BYTES);
+            tma_load_2d(&tm.resid, ebar0, sbuf0, n + 32, row0);
+          }
         }
       }
 
       // ---- optional post-LayerNorm of the final value (norm1 / norm3 of the next transformer block)
-      if (g.ln2_gamma) {
+      if (F_LN2) {
         const float mean2 = sum2 * (1.0f / (float)g.N);
         const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / (float)g.N) - mean2 * mean2, 0.f) + 1e-5f);
         for (int c = 0; c < n_chunks; ++c) {
@@ -534,9 +601,12 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (lane == 0) bulk_wait_read0();
+          if (lane == 0) {  // alternate the two staging buffers
+            if (dual) bulk_wait_read0();
+            else bulk_wait_read1();
+          }
           __syncwarp();
-          stage_store_b16(&tm.out_ln, hbuf, lane, v, n, row0);
+          stage_store_b16(&tm.out_ln, sbuf0 + (c & 1) * EPI_F32_BYTES, lane, v, n, row0);
         }
       }
       tc_fence_before();
@@ -547,6 +617,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();  // no CTA leaves while a peer can still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
