@@ -136,16 +136,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       mbar_wait(bar_s, ph, 16);
       tc_fence_after();
       float mx = -INFINITY;
+      const bool full = kvalid == TK;  // warp-uniform: full key tiles skip all masking arithmetic
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t acc[32];
         tmem_ld32(tS + lane_addr + c * 32, acc);
-        if (c * 32 < kvalid) {
+        if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = (c * 32 + i < kvalid) ? __uint_as_float(acc[i]) : -INFINITY;
-            mx = fmaxf(mx, x);
-          }
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(acc[i]));
+        } else {
+          const int vc = kvalid - c * 32;  // valid keys in this chunk (may be <= 0)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < vc ? __uint_as_float(acc[i]) : -INFINITY);
         }
       }
       const float m_new = fmaxf(m_run, mx * scale_log2e);
@@ -168,11 +170,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         uint32_t acc[32];
         tmem_ld32(tS + lane_addr + c * 32, acc);
         float pv[32];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pr = (c * 32 + i < kvalid) ? fast_exp2(fmaf(__uint_as_float(acc[i]), scale_log2e, -m_new)) : 0.f;
-          pv[i] = pr;
-          lsum += pr;
+          for (int i = 0; i < 32; ++i) {
+            pv[i] = fast_exp2(fmaf(__uint_as_float(acc[i]), scale_log2e, -m_new));
+            lsum += pv[i];
+          }
+        } else {
+          const int vc = kvalid - c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float t = fmaf(__uint_as_float(acc[i]), scale_log2e, -m_new);
+            pv[i] = fast_exp2(i < vc ? t : -INFINITY);  // ex2(-inf) = 0: no branch around the MUFU
+            lsum += pv[i];
+          }
         }
         // P[row][key]: K-major SWIZZLE_128B, tile = key / 64, 16-byte chunk = (key % 64) / 8
         const uint32_t tile = sP + (c >> 1) * TILE_BYTES;

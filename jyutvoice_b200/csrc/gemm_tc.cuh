@@ -29,7 +29,7 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_F32_BYTES = 32 * 32 * 4;  // 4 KB: 32 rows x 128 B, SWIZZLE_128B
 constexpr int EPI_B16_BYTES = 32 * 32 * 2;  // 2 KB: 32 rows x 64 B, SWIZZLE_64B
-constexpr int EPI_BYTES_PER_WARP = 2 * EPI_F32_BYTES;  // two 4 KB staging buffers per epilogue warp (double buffering)
+constexpr int EPI_BYTES_PER_WARP = 2 * EPI_F32_BYTES + EPI_B16_BYTES;  // residual-in 4 KB | fp32-out 4 KB | bf16-out 2 KB
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TMEM_COLS = 512;
@@ -352,7 +352,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const uint32_t empty_bar = bars + 8 * MAX_STAGES;      // MAX_STAGES x 8 B
   const uint32_t tfull_bar = bars + 16 * MAX_STAGES;     // 2 x 8 B
   const uint32_t tempty_bar = tfull_bar + 16;            // 2 x 8 B
-  const uint32_t epi_bar = tempty_bar + 16;              // EPI_WARPS x 2 x 8 B (one per staging buffer)
+  const uint32_t epi_bar = tempty_bar + 16;              // EPI_WARPS x 16 B (residual-load barrier per warp)
   const uint32_t tmem_slot = epi_bar + 16 * EPI_WARPS;   // 4 B
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -456,22 +456,27 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     const int e = warp - 4;
     const int q = e & 3;        // TMEM lane quarter (warp index % 4)
     const int grp = e >> 2;     // accumulator stage served by this warp
-    // Two 4 KB staging buffers.  Normal mode: chunk c lives entirely in buffer c & 1 (residual in, fp32 or bf16
-    // out), so the TMA load of chunk c + 1 and the TMA store of chunk c - 1 overlap the math of chunk c.
-    // Dual-output mode (fp32 traffic AND a bf16 copy): buffer 0 = fp32, buffer 1 = bf16, no overlap.
-    const uint32_t sbuf0 = smem_epi + e * EPI_BYTES_PER_WARP;
-    const uint32_t ebar0 = epi_bar + 16 * e;
-    uint32_t ephase = 0;  // bit b = phase parity of staging buffer b's mbarrier
-    const bool dual = (F_RESID || F_F32) && F_OACT;
+    // Staging per warp: R = residual in (TMA load), OF = fp32 out, OB = bf16 out (TMA stores).  R is refilled
+    // with chunk c + 1 as soon as every lane has read chunk c, independent of the stores; the output buffers
+    // are waited for (cp.async.bulk.wait_group.read) only right before they are rewritten, i.e. after the math.
+    // Kernels without fp32 output alternate OF / OB as two bf16 buffers and never wait for the latest store.
+    const uint32_t sR = smem_epi + e * EPI_BYTES_PER_WARP;
+    const uint32_t sOF = sR + EPI_F32_BYTES;
+    const uint32_t sOB = sOF + EPI_F32_BYTES;
+    const uint32_t ebar = epi_bar + 16 * e;
+    uint32_t ephase = 0;
     uint32_t acc_phase = 0;
     const int n_chunks = p.block_n >> 5;
-    const bool has_f32_in = F_RESID;
     int local_tile = 0;
     for (int unit = unit0; unit < p.num_units; unit += unit_step, ++local_tile) {
       if ((local_tile & 1) != grp) continue;
       const int m0 = ((unit / p.n_tiles_n) * csz + cta_rank) * BLOCK_M;
       const int n0 = (unit % p.n_tiles_n) * p.block_n;
       const int row0 = m0 + q * 32;  // first row (view coordinates) of this warp's 32-row slab
+      if (F_RESID && lane == 0) {  // residual of the first chunk: in flight while the accumulator is still being computed
+        mbar_expect_tx(ebar, EPI_F32_BYTES);
+        tma_load_2d(&tm.resid, ebar, sR, n0, row0);
+      }
       mbar_wait(tfull_bar + 8 * grp, acc_phase, 4);
       acc_phase ^= 1;
       tc_fence_after();
@@ -506,30 +511,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       // ---- main pass
       float sum2 = 0.f, sq2 = 0.f;
       const int n_chunks_valid = (g.N - n0 + 31) / 32 < n_chunks ? (g.N - n0 + 31) / 32 : n_chunks;
-      if (has_f32_in && lane == 0) {  // residual of the first chunk
-        bulk_wait_read0();
-        mbar_expect_tx(ebar0, EPI_F32_BYTES);
-        tma_load_2d(&tm.resid, ebar0, sbuf0, n0, row0);
-      }
       for (int c = 0; c < n_chunks_valid; ++c) {
         const int n = n0 + c * 32;
         const int n_valid = g.N - n < 32 ? g.N - n : 32;
-        const int bi = dual ? 0 : (c & 1);
-        const uint32_t fbuf = sbuf0 + bi * EPI_F32_BYTES;
-        const uint32_t hbuf = dual ? sbuf0 + EPI_F32_BYTES : fbuf;
-        if (lane == 0) {
-          if (has_f32_in) {
-            if (!dual && c + 1 < n_chunks_valid) {  // prefetch the next chunk's residual into the other buffer
-              bulk_wait_read0();                    // ... once the store of chunk c - 1 has left it
-              mbar_expect_tx(ebar0 + 8 * (bi ^ 1), EPI_F32_BYTES);
-              tma_load_2d(&tm.resid, ebar0 + 8 * (bi ^ 1), sbuf0 + (bi ^ 1) * EPI_F32_BYTES, n + 32, row0);
-            }
-          } else if (dual) {
-            bulk_wait_read0();
-          } else {
-            bulk_wait_read1();  // the store of chunk c - 2 used this buffer
-          }
-        }
         uint32_t acc[32];
         tmem_ld32(taddr + c * 32, acc);
         float v[32];
@@ -542,19 +526,19 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-        __syncwarp();  // lane 0's wait_group.read precedes every lane's staging writes
-        if (has_f32_in) {
-          mbar_wait(ebar0 + 8 * bi, (ephase >> bi) & 1u, 5);
-          ephase ^= 1u << bi;
+        if (F_RESID) {
+          mbar_wait(ebar, ephase, 5);
+          ephase ^= 1;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 r = lds128(fbuf + swz128(lane, j));
+            const float4 r = lds128(sR + swz128(lane, j));
             v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
           }
-        }
-        if (F_F32) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sts128(fbuf + swz128(lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();  // every lane has read R: refill it with the next chunk's residual
+          if (lane == 0 && c + 1 < n_chunks_valid) {
+            mbar_expect_tx(ebar, EPI_F32_BYTES);
+            tma_load_2d(&tm.resid, ebar, sR, n + 32, row0);
+          }
         }
         if (F_LN2) {  // keep the final value in TMEM for the post-LayerNorm sweep
 #pragma unroll
@@ -564,6 +548,17 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             sq2 = fmaf(v[j], v[j], sq2);
           }
           tmem_st32(taddr + c * 32, acc);
+        }
+        // output staging: wait (late) for the stores that last used the buffers
+        const uint32_t hbuf = F_F32 ? sOB : ((c & 1) ? sOB : sOF);
+        if (lane == 0) {
+          if (F_F32) bulk_wait_read0();
+          else bulk_wait_read1();
+        }
+        __syncwarp();
+        if (F_F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128(sOF + swz128(lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (F_OACT) {
           if (g.act2 != ACT_NONE) act32(v, g.act2, g.act2_param, g.act2_vec ? g.act2_vec + n : nullptr, n_valid);
@@ -575,14 +570,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (F_F32) tma_store_2d(&tm.out_f32, fbuf, n, row0);
+          if (F_F32) tma_store_2d(&tm.out_f32, sOF, n, row0);
           if (F_OACT) tma_store_2d(&tm.out_act, hbuf, n, row0);
           bulk_commit();
-          if (dual && has_f32_in && c + 1 < n_chunks_valid) {  // no second fp32 buffer in dual mode: load after the store
-            bulk_wait_read0();
-            mbar_expect_tx(ebar0, EPI_F32_BYTES);
-            tma_load_2d(&tm.resid, ebar0, sbuf0, n + 32, row0);
-          }
         }
       }
 
@@ -601,12 +591,12 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (lane == 0) {  // alternate the two staging buffers
-            if (dual) bulk_wait_read0();
+          if (lane == 0) {  // alternate OF / OB as bf16 buffers; the first two chunks wait for the main pass's stores
+            if (c < 2) bulk_wait_read0();
             else bulk_wait_read1();
           }
           __syncwarp();
-          stage_store_b16(&tm.out_ln, sbuf0 + (c & 1) * EPI_F32_BYTES, lane, v, n, row0);
+          stage_store_b16(&tm.out_ln, (c & 1) ? sOB : sOF, lane, v, n, row0);
         }
       }
       tc_fence_before();

@@ -27,7 +27,7 @@ cases = [
     ("hift s0  N=256  K=7x256 bf16", M // 4, 256, 256, 7, 16),
 ]
 for name, m, n, k, taps, mode in cases:
-    if only and not name.startswith(only):
+    if only and not (name == only[1:] if only.startswith('=') else name.startswith(only)):
         continue
     ms = ctypes.c_double()
     rc = L.jv_bench_gemm(m, n, k, taps, mode, iters, ctypes.byref(ms))
