@@ -1,5 +1,6 @@
 """jyutvoice_b200: B200-native (sm_100a) CFM + HiFT hot path behind the reference's Python API."""
 from .flow_matching import CausalConditionalCFM, CausalConditionalDecoder  # noqa: F401
 from .hifigan import HiFTGenerator, ConvRNNF0Predictor  # noqa: F401
+from .tts import JyutVoiceTTS  # noqa: F401
 
-__all__ = ["CausalConditionalCFM", "CausalConditionalDecoder", "HiFTGenerator", "ConvRNNF0Predictor"]
+__all__ = ["CausalConditionalCFM", "CausalConditionalDecoder", "HiFTGenerator", "ConvRNNF0Predictor", "JyutVoiceTTS"]

@@ -46,6 +46,53 @@ def hift_mel(seed, B, T):
     return torch.randn(B, 80, T, generator=g) * 2 - 5
 
 
+def synth_inputs(seed, Tx):
+    """~50 token ids, random ids per stream, random speaker embedding."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(1, 97, (1, Tx), generator=g)
+    lang = torch.randint(0, 4, (1, Tx), generator=g)
+    tone = torch.randint(0, 7, (1, Tx), generator=g)
+    word_pos = torch.randint(0, 4, (1, Tx), generator=g)
+    syllable_pos = torch.randint(0, 4, (1, Tx), generator=g)
+    spk_embed = torch.randn(1, 192, generator=g)
+    return x, torch.tensor([Tx]), lang, tone, word_pos, syllable_pos, spk_embed
+
+
+def synth_golden():
+    """Runs the reference's real TextEncoder + DurationPredictor + synthesise.  The encoder / dp outputs are stored so
+    the GPU test can stand in for those two (out-of-scope, host-side) modules without their 25 M weights."""
+    import types
+    ref_shims.install()
+    from jyutvoice.models.jyutvoice_tts import JyutVoiceTTS
+    from jyutvoice.models.text_encoder import TextEncoder
+    from jyutvoice.models.duration_predictor import DurationPredictor
+    torch.manual_seed(1234)
+    enc_params = types.SimpleNamespace(n_feats=80, n_channels=192, filter_channels=768, filter_channels_dp=256, n_heads=2,
+                                       n_layers=6, kernel_size=3, p_dropout=0.1, gin_channels=192, prenet=True)
+    encoder = TextEncoder(encoder_type="RoPE Encoder", encoder_params=enc_params, n_vocab=97, n_lang=4, n_tone=7)
+    dp = DurationPredictor(in_channels=576, filter_channels=256, kernel_size=3, p_dropout=0.1, gin_channels=192)
+    cfm = ref_shims.build_reference_cfm()
+    cfm.load_state_dict(weights.make_estimator_state_dict(), strict=True)
+    tts = JyutVoiceTTS(encoder=encoder, decoder=cfm, dp=dp, output_size=80, spk_embed_dim=192)
+    aff = weights.make_spk_affine_state_dict()
+    tts.spk_embed_affine_layer.load_state_dict(aff)
+    tts.eval()
+    for name, seed, Tx, ls, n, prompt in (("synth_c1", 0, 51, 1.0, 10, 0), ("synth_prompt", 1, 21, 2.0, 4, 17)):
+        inp = synth_inputs(seed, Tx)
+        g = torch.Generator().manual_seed(seed + 500)
+        pf = torch.randn(1, prompt, 80, generator=g) if prompt else None
+        ph = torch.randn(1, prompt, 80, generator=g) if prompt else None
+        with torch.no_grad():
+            ex, emu, emask = encoder(*inp)
+            logw = dp(ex, emask, inp[-1])
+            out = tts.synthesise(*inp, prompt_feat=pf, prompt_h=ph, n_timesteps=n, temperature=1.0, length_scale=ls)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, Tx=Tx, length_scale=ls, n_timesteps=n, prompt=prompt,
+                            enc_x=ex.numpy(), enc_mu=emu.numpy(), enc_mask=emask.numpy(), logw=logw.numpy(),
+                            mel_lengths=out["mel_lengths"].numpy(), attn=out["attn"].numpy().astype(np.uint8),
+                            encoder_outputs=out["encoder_outputs"].numpy(), decoder_outputs=out["decoder_outputs"].numpy())
+        print(name, "T =", int(out["mel_lengths"][0]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -125,6 +172,8 @@ def main():
         cases[f"c{ci}_y_mask"] = y_mask.numpy()
     cases["n_cases"] = 5
     np.savez_compressed(os.path.join(OUT, "lengths.npz"), **cases)
+    # ---------------- end to end: the reference's JyutVoiceTTS.synthesise (config 1 of BASELINE.json) ----------------
+    synth_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
