@@ -1,22 +1,24 @@
 // tcgen05 multi-head attention for the estimator's transformer blocks (bf16 mode).
 // 8 heads x 64, non-causal, keys masked by the row length (decoder.py:955-959: -1e10 bias on padded keys).
-// One CTA = 128 queries of one (row, head); keys are consumed in tiles of 128 with an online softmax:
-//   S = Q K^T      tcgen05.mma M=128 N=128 K=64      (Q, K tiles by TMA, 128B swizzle, K-major)
+// One CTA = 128 queries of one (row, head); keys are consumed in tiles of 64 with an online softmax:
+//   S = Q K^T      tcgen05.mma M=128 N=64  K=64      (Q, K tiles by TMA, 128B swizzle, K-major)
 //   P = softmax    one thread per query row: tcgen05.ld S, exp2, running max / sum, P -> smem (bf16, K-major)
-//   O += P V       tcgen05.mma M=128 N=64  K=128     (V tile by TMA is the MN-major B operand as it lies in memory)
+//   O += P V       tcgen05.mma M=128 N=64  K=64      (V tile by TMA is the MN-major B operand as it lies in memory)
 // O stays in TMEM across key tiles and is rescaled in place (tcgen05.ld / st) when the running max moves.
-// Two CTAs fit per SM (80 KB smem, 256 TMEM columns each), which overlaps one CTA's softmax with the other's MMAs.
+// Four CTAs fit per SM (48 KB smem, 128 TMEM columns each): while one CTA's softmax threads work, the others' MMAs,
+// TMA loads and barrier round trips are in flight.
 #pragma once
 #include "gemm_tc.cuh"
 
 namespace jv {
 namespace attn {
 
-constexpr int TQ = 128, TK = 128, HD = 64;
-constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: one 128 x 64 bf16 tile
-constexpr int SMEM_BYTES = 1024 + 3 * TILE_BYTES + 2 * TILE_BYTES + 128;
+constexpr int TQ = 128, TK = 64, HD = 64;
+constexpr int Q_BYTES = TQ * HD * 2;   // 16 KB: 128 x 64 bf16 (also the P tile: 128 queries x 64 keys)
+constexpr int KV_BYTES = TK * HD * 2;  // 8 KB: 64 x 64 bf16
+constexpr int SMEM_BYTES = 1024 + 2 * Q_BYTES + 2 * KV_BYTES + 128;  // Q, P, K, V: 48 KB -> four CTAs per SM
 constexpr int THREADS = 160;
-constexpr int TMEM_COLS = 256;  // S: columns [0,128), O: columns [128,192)
+constexpr int TMEM_COLS = 128;  // S: columns [0,64), O: columns [64,128)
 
 // MN-major SWIZZLE_128B descriptor for the V tile [keys][64 d]: rows of 128 B (64 d), 8-key groups 1024 B apart
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
@@ -35,8 +37,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int ldo, const int* __restrict__ row_off,
+__global__ void __launch_bounds__(THREADS, 4)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV, bf16* __restrict__ out, int ldo, const int* __restrict__ row_off,
                     const int* __restrict__ row_len, float scale_log2e) {
   using namespace tc;
   const int r = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
@@ -48,8 +50,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = base + 2 * TILE_BYTES, sP = base + 3 * TILE_BYTES;  // sP: 2 tiles
-  const uint32_t bars = sP + 2 * TILE_BYTES;
+  const uint32_t sQ = base, sP = base + Q_BYTES, sK = base + 2 * Q_BYTES, sV = sK + KV_BYTES;
+  const uint32_t bars = sV + KV_BYTES;
   const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_s = bars + 24, bar_p = bars + 32, bar_o = bars + 40;
   const uint32_t tmem_slot = bars + 48;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
@@ -74,19 +76,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base, tO = tmem_base + 64;
 
   if (warp == 0) {
     if (lane == 0) {
       // instruction descriptors: bf16 x bf16 -> fp32, M = 128; S: N = 128 both K-major; PV: N = 64, B MN-major (bit 16)
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TK >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
-      mbar_expect_tx(bar_q, TILE_BYTES);
+      mbar_expect_tx(bar_q, Q_BYTES);
       tma_load_2d(&tmQKV, bar_q, sQ, h * HD, off + q0);
-      mbar_expect_tx(bar_k, TILE_BYTES);
-      tma_load_2d(&tmQKV, bar_k, sK, 512 + h * HD, off);
-      mbar_expect_tx(bar_v, TILE_BYTES);
-      tma_load_2d(&tmQKV, bar_v, sV, 1024 + h * HD, off);
+      mbar_expect_tx(bar_k, KV_BYTES);
+      tma_load_2d(&tmKV, bar_k, sK, 512 + h * HD, off);
+      mbar_expect_tx(bar_v, KV_BYTES);
+      tma_load_2d(&tmKV, bar_v, sV, 1024 + h * HD, off);
       mbar_wait(bar_q, 0, 10);
       auto issue_s = [&](int j) {  // S_j = Q K_j^T; afterwards the K buffer is reloaded with tile j + 1
         mbar_wait(bar_k, j & 1, 11);
@@ -101,16 +103,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         const uint32_t ph = j & 1;
         if (j + 1 < nt) {  // K buffer is free once S_j has been computed
           mbar_wait(bar_s, ph, 12);
-          mbar_expect_tx(bar_k, TILE_BYTES);
-          tma_load_2d(&tmQKV, bar_k, sK, 512 + h * HD, off + (j + 1) * TK);
+          mbar_expect_tx(bar_k, KV_BYTES);
+          tma_load_2d(&tmKV, bar_k, sK, 512 + h * HD, off + (j + 1) * TK);
         }
         mbar_wait(bar_p, ph, 13);  // softmax j done: P_j in smem, O rescaled, S buffer free
         tc_fence_after();
         mbar_wait(bar_v, ph, 14);
 #pragma unroll
         for (int s = 0; s < TK / 16; ++s) {
-          // A = P: two K-major 128x64 tiles; step s covers keys [16 s, 16 s + 16)
-          const uint64_t adesc = make_smem_desc(sP + (s >> 2) * TILE_BYTES) + 2 * (s & 3);
+          // A = P: one K-major 128 x 64 tile; step s covers keys [16 s, 16 s + 16)
+          const uint64_t adesc = make_smem_desc(sP) + 2 * s;
           const uint64_t bdesc = make_smem_desc_mn(sV + s * 2048);
           umma_bf16(tO, adesc, bdesc, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
         }
@@ -118,8 +120,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
         if (j + 1 < nt) {
           issue_s(j + 1);  // queued right behind PV_j: the next softmax starts while O is still accumulating
           mbar_wait(bar_o, ph, 15);  // V buffer (and P) free once O has been updated
-          mbar_expect_tx(bar_v, TILE_BYTES);
-          tma_load_2d(&tmQKV, bar_v, sV, 1024 + h * HD, off + (j + 1) * TK);
+          mbar_expect_tx(bar_v, KV_BYTES);
+          tma_load_2d(&tmKV, bar_v, sV, 1024 + h * HD, off + (j + 1) * TK);
         }
       }
     }
@@ -138,7 +140,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       float mx = -INFINITY;
       const bool full = kvalid == TK;  // warp-uniform: full key tiles skip all masking arithmetic
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < TK / 32; ++c) {
         uint32_t acc[32];
         tmem_ld32(tS + lane_addr + c * 32, acc);
         if (full) {
@@ -166,7 +168,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
       }
       float lsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < TK / 32; ++c) {
         uint32_t acc[32];
         tmem_ld32(tS + lane_addr + c * 32, acc);
         float pv[32];
@@ -185,12 +187,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             lsum += pv[i];
           }
         }
-        // P[row][key]: K-major SWIZZLE_128B, tile = key / 64, 16-byte chunk = (key % 64) / 8
-        const uint32_t tile = sP + (c >> 1) * TILE_BYTES;
+        // P[row][key]: K-major SWIZZLE_128B, 16-byte chunk = key / 8
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          const int chunk = (c & 1) * 4 + g8;
-          sts128u(tile + swz128(row, chunk), pack_bf16(pv[8 * g8], pv[8 * g8 + 1]), pack_bf16(pv[8 * g8 + 2], pv[8 * g8 + 3]),
+          const int chunk = c * 4 + g8;
+          sts128u(sP + swz128(row, chunk), pack_bf16(pv[8 * g8], pv[8 * g8 + 1]), pack_bf16(pv[8 * g8 + 2], pv[8 * g8 + 3]),
                   pack_bf16(pv[8 * g8 + 4], pv[8 * g8 + 5]), pack_bf16(pv[8 * g8 + 6], pv[8 * g8 + 7]));
         }
       }
@@ -239,9 +240,10 @@ static inline void launch_attention_tc(TmapCache& cache, const void* qkv, void* 
     JV_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
     attr = true;
   }
-  const CUtensorMap& tm = cache.get(qkv, 1536, M_alloc, 1536 * 2, 64, 128, 0);
+  const CUtensorMap tm = cache.get(qkv, 1536, M_alloc, 1536 * 2, 64, attn::TQ, 0);
+  const CUtensorMap tmkv = cache.get(qkv, 1536, M_alloc, 1536 * 2, 64, attn::TK, 0);
   dim3 grid(cdiv(Tmax_len, attn::TQ), 8, R);
-  attn::attention_tc_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tm, (bf16*)out, 512, row_off, row_len,
+  attn::attention_tc_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tm, tmkv, (bf16*)out, 512, row_off, row_len,
                                                                           0.125f * 1.4426950408889634f);
   JV_LAUNCHED();
 }
