@@ -75,6 +75,15 @@ static const KernelEntry* kernel_table() {
   return t;
 }
 
+static bool use_wres() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_WRES");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 bool gemm_tc_supported(const GemmDesc& g) {
@@ -117,18 +126,72 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   const int m_tiles = cdiv(g.M, tc::BLOCK_M);
   p.num_tiles = m_tiles * p.n_tiles_n;
   p.b_stage_bytes = round_up(p.block_n * tc::BLOCK_K * 2, 1024);
-  const int fixed = 1024 + tc::EPI_WARPS * tc::EPI_BYTES_PER_WARP + tc::BAR_BYTES;
-  p.stages = (tc::SMEM_LIMIT - fixed) / (tc::A_STAGE_BYTES + p.b_stage_bytes);
+  const long Ktot = (long)g.n_taps * g.K_tap;
+  const int k_iters = (int)(Ktot / tc::BLOCK_K);
+  const int epi = (g.ln1_gamma ? tc::EPI_LN1 : 0) | (g.resid ? tc::EPI_RESID : 0) | (g.out_f32 ? tc::EPI_F32 : 0) |
+                  (g.out_act ? tc::EPI_OACT : 0) | (g.ln2_gamma ? tc::EPI_LN2 : 0);
+  // weight-resident mode: bf16-only epilogue, whole weight tile <= 128 KB, enough m-tiles per CTA to amortise it
+  const int ctas_per_ntile = num_sms / p.n_tiles_n;
+  p.wres = (epi == tc::EPI_OACT && k_iters * p.b_stage_bytes <= 131072 && ctas_per_ntile >= 1 && m_tiles >= 4 * ctas_per_ntile &&
+            use_wres())
+               ? 1
+               : 0;
+  const bool wide = epi == tc::EPI_OACT;  // bf16-only epilogue: 16 epilogue warps, small staging
+  const int n_epi_warps = wide ? tc::EPI_WARPS_MAX : tc::EPI_WARPS;
+  p.epi_bytes_per_warp = wide ? (p.wres ? tc::EPI_B16_BYTES : 2 * tc::EPI_B16_BYTES)
+                              : ((epi & tc::EPI_OACT) ? tc::EPI_BYTES_PER_WARP : 2 * tc::EPI_F32_BYTES);
+  // per-column vector cache (only when the CTA's n-tile is fixed), in priority order while smem remains
+  const bool n_fixed = p.n_tiles_n == 1 || p.wres;
+  const int vbytes = p.block_n * 4;
+  int want_bias = (n_fixed && g.bias) ? vbytes : 0, want_ln1 = (n_fixed && g.ln1_gamma) ? 2 * vbytes : 0,
+      want_ln2 = (n_fixed && g.ln2_gamma) ? 2 * vbytes : 0, want_act = (n_fixed && g.act_vec) ? vbytes : 0,
+      want_act2 = (n_fixed && g.act2_vec) ? vbytes : 0;
+  const int fixed_novec = 1024 + n_epi_warps * p.epi_bytes_per_warp + tc::BAR_BYTES;
+  {
+    // smem left after the pipeline the kernel would get WITHOUT any vector cache (never trade a pipeline stage for it)
+    int ring = p.wres ? tc::A_STAGE_BYTES : tc::A_STAGE_BYTES + p.b_stage_bytes;
+    int avail = tc::SMEM_LIMIT - fixed_novec - (p.wres ? k_iters * p.b_stage_bytes : 0);
+    int st = avail / ring;
+    if (st > tc::MAX_STAGES) st = tc::MAX_STAGES;
+    int spare = avail - st * ring;
+    auto take = [&](int& w) { if (w <= spare) spare -= w; else w = 0; };
+    take(want_bias); take(want_ln1); take(want_ln2); take(want_act); take(want_act2);
+  }
+  const int vec_total = want_bias + want_ln1 + want_ln2 + want_act + want_act2;
+  const int fixed = fixed_novec + vec_total;
+  if (p.wres) {
+    p.b_region_bytes = k_iters * p.b_stage_bytes;
+    p.stages = (tc::SMEM_LIMIT - fixed - p.b_region_bytes) / tc::A_STAGE_BYTES;
+  } else {
+    p.stages = (tc::SMEM_LIMIT - fixed) / (tc::A_STAGE_BYTES + p.b_stage_bytes);
+  }
   if (p.stages > tc::MAX_STAGES) p.stages = tc::MAX_STAGES;
   JV_REQUIRE(p.stages >= 2, JV_ERR_STATE, "not enough shared memory for the GEMM pipeline");
-  const int smem = fixed + p.stages * (tc::A_STAGE_BYTES + p.b_stage_bytes);
-  const long Ktot = (long)g.n_taps * g.K_tap;
+  if (!p.wres) p.b_region_bytes = p.stages * p.b_stage_bytes;
+  const int smem = fixed + p.stages * tc::A_STAGE_BYTES + p.b_region_bytes;
+  {  // vector cache sits after the barrier block: offsets from the aligned base
+    int off = p.stages * tc::A_STAGE_BYTES + p.b_region_bytes + n_epi_warps * p.epi_bytes_per_warp + tc::BAR_BYTES;
+    auto place = [&](int want) { int o = want ? off : 0; off += want; return o; };
+    p.vec_bias = place(want_bias);
+    p.vec_ln1 = place(want_ln1);
+    p.vec_ln2 = place(want_ln2);
+    p.vec_act = place(want_act);
+    p.vec_act2 = place(want_act2);
+  }
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("JYUTVOICE_B200_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   if (cache.maps.size() > 4096) cache.maps.clear();  // before the gets: references must stay valid below
   tc::TcMaps tm;
   tm.a0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], (long)g.lda[0] * 2, tc::BLOCK_K, tc::BLOCK_M, 0);
   tm.a1 = g.A[1] ? cache.get(g.A[1], g.K_tap, g.a_rows[1], (long)g.lda[1] * 2, tc::BLOCK_K, tc::BLOCK_M, 0) : tm.a0;
-  p.cluster = (m_tiles >= 2 && p.block_n % 16 == 0 && use_cluster()) ? 2 : 1;
-  p.num_units = cdiv(m_tiles, p.cluster) * p.n_tiles_n;
+  p.cluster = (!p.wres && m_tiles >= 2 && p.block_n % 16 == 0 && use_cluster()) ? 2 : 1;
+  p.num_units = p.wres ? m_tiles : cdiv(m_tiles, p.cluster) * p.n_tiles_n;
   tm.w = cache.get(g.W, Ktot, g.N, Ktot * 2, tc::BLOCK_K, p.block_n / p.cluster, 0);
   tm.resid = g.resid ? out_view(cache, g, g.resid, g.ldr, 4, 1) : tm.a0;
   tm.out_f32 = g.out_f32 ? out_view(cache, g, g.out_f32, g.ldo, 4, 1) : tm.a0;
@@ -136,6 +199,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   tm.out_ln = g.out_ln ? out_view(cache, g, g.out_ln, g.ldo3, 2, 2) : tm.a0;
   int grid = p.num_units * p.cluster < num_sms ? p.num_units * p.cluster : num_sms;
   grid -= grid % p.cluster;
+  if (p.wres) grid = ctas_per_ntile * p.n_tiles_n;
   ProfileState& ps = profile_state();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ps.on) {
@@ -146,7 +210,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.blockDim = dim3(wide ? tc::NUM_THREADS_WIDE : tc::NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -156,8 +220,6 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const int epi = (g.ln1_gamma ? tc::EPI_LN1 : 0) | (g.resid ? tc::EPI_RESID : 0) | (g.out_f32 ? tc::EPI_F32 : 0) |
-                  (g.out_act ? tc::EPI_OACT : 0) | (g.ln2_gamma ? tc::EPI_LN2 : 0);
   KernelFn fn = kernel_table()[N_KERNELS - 1].fn;  // generic
   for (int i = 0; i < N_KERNELS - 1; ++i)
     if (kernel_table()[i].epi == epi) fn = kernel_table()[i].fn;

@@ -26,7 +26,8 @@ constexpr int BLOCK_K = 64;  // bf16 elements: 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;       // epilogue warps of the general kernels (two groups of four)
+constexpr int EPI_WARPS_MAX = 16;  // bf16-only epilogues run two warps per (group, lane quarter): even / odd column chunks
 constexpr int EPI_F32_BYTES = 32 * 32 * 4;  // 4 KB: 32 rows x 128 B, SWIZZLE_128B
 constexpr int EPI_B16_BYTES = 32 * 32 * 2;  // 2 KB: 32 rows x 64 B, SWIZZLE_64B
 constexpr int EPI_BYTES_PER_WARP = 2 * EPI_F32_BYTES + EPI_B16_BYTES;  // residual-in 4 KB | fp32-out 4 KB | bf16-out 2 KB
@@ -34,6 +35,7 @@ constexpr int BAR_BYTES = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS_WIDE = 128 + 32 * EPI_WARPS_MAX;  // 640
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -206,8 +208,8 @@ __device__ __forceinline__ void add_vec32(float (&v)[32], const float* __restric
 #pragma unroll
   for (int j8 = 0; j8 < 4; ++j8) {
     if (j8 * 8 + 8 <= n_valid) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(pv + j8 * 8));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(pv + j8 * 8 + 4));
+      const float4 a = *reinterpret_cast<const float4*>(pv + j8 * 8);
+      const float4 b = *reinterpret_cast<const float4*>(pv + j8 * 8 + 4);
       v[j8 * 8 + 0] += a.x; v[j8 * 8 + 1] += a.y; v[j8 * 8 + 2] += a.z; v[j8 * 8 + 3] += a.w;
       v[j8 * 8 + 4] += b.x; v[j8 * 8 + 5] += b.y; v[j8 * 8 + 6] += b.z; v[j8 * 8 + 7] += b.w;
     }
@@ -217,8 +219,8 @@ __device__ __forceinline__ void ln_affine32(float (&v)[32], float mean, float rs
                                             const float* __restrict__ beta) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + j4 * 4));
-    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + j4 * 4));
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + j4 * 4);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + j4 * 4);
     v[j4 * 4 + 0] = fmaf((v[j4 * 4 + 0] - mean) * rstd, gm.x, bt.x);
     v[j4 * 4 + 1] = fmaf((v[j4 * 4 + 1] - mean) * rstd, gm.y, bt.y);
     v[j4 * 4 + 2] = fmaf((v[j4 * 4 + 2] - mean) * rstd, gm.z, bt.z);
@@ -260,8 +262,8 @@ __device__ __forceinline__ void act32(float (&v)[32], int act, float prm, const 
 #pragma unroll
       for (int j8 = 0; j8 < 4; ++j8) {
         if (j8 * 8 + 8 <= n_valid) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(vec + j8 * 8));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(vec + j8 * 8 + 4));
+          const float4 a0 = *reinterpret_cast<const float4*>(vec + j8 * 8);
+          const float4 a1 = *reinterpret_cast<const float4*>(vec + j8 * 8 + 4);
           const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -292,7 +294,18 @@ struct TcParams {
   int block_n, n_tiles_n, num_tiles, stages, b_stage_bytes;
   int cluster;    // CTAs per cluster (1 or 2): the CTAs of a cluster work on consecutive m-tiles of the same n-tile and
                   // each loads 1/cluster of the weight tile, multicast to all of them (halves the L2 -> SM weight traffic)
-  int num_units;  // ceil(m_tiles / cluster) * n_tiles_n
+  int num_units;  // ceil(m_tiles / cluster) * n_tiles_n   (weight-resident mode: m_tiles)
+  // Weight-resident mode (K_total * block_n * 2 <= 128 KB, bf16-only output: QKV, FF1): a CTA is bound to one n-tile,
+  // loads its whole weight tile into smem ONCE and streams only activation tiles through the ring.  The kernel is
+  // bound by SM <-> L2 traffic, and the weight tile is 2/3 of a 128 x 256 tile's operand bytes.
+  int wres;
+  int b_region_bytes;      // ring: stages * b_stage_bytes; resident: k_iters * b_stage_bytes
+  int epi_bytes_per_warp;  // 10 KB (residual + fp32 + bf16 staging) or 4 KB (two bf16 buffers)
+  // Per-column vectors cached in smem once per CTA (byte offsets from the aligned smem base; 0 = read from global).
+  // Only when the CTA's n-tile is fixed (one n-tile, or weight-resident mode).  With 227 KB of smem there is no L1,
+  // so every uncached read of bias / gamma / beta / alpha is an L2 round trip inside the epilogue's dependency chain.
+  int vec_bias, vec_ln1, vec_ln2, vec_act, vec_act2;
+  int debug;               // experiments only (JYUTVOICE_B200_DEBUG): 1 = no output stores, 2 = no epilogue at all
 };
 
 // byte offset of 16-byte chunk j of row r inside a staging buffer
@@ -334,26 +347,29 @@ __device__ __forceinline__ void stage_store_b16(const CUtensorMap* tm, uint32_t 
 constexpr int EPI_LN1 = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_OACT = 8, EPI_LN2 = 16;
 
 template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(EPI == EPI_OACT ? NUM_THREADS_WIDE : NUM_THREADS, 1)
 gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const TcParams p) {
   const bool F_LN1 = EPI >= 0 ? (EPI & EPI_LN1) != 0 : g.ln1_gamma != nullptr;
   const bool F_RESID = EPI >= 0 ? (EPI & EPI_RESID) != 0 : g.resid != nullptr;
   const bool F_F32 = EPI >= 0 ? (EPI & EPI_F32) != 0 : g.out_f32 != nullptr;
   const bool F_OACT = EPI >= 0 ? (EPI & EPI_OACT) != 0 : g.out_act != nullptr;
   const bool F_LN2 = EPI >= 0 ? (EPI & EPI_LN2) != 0 : g.ln2_gamma != nullptr;
+  constexpr int N_EPI_WARPS = EPI == EPI_OACT ? EPI_WARPS_MAX : EPI_WARPS;
+  constexpr int N_SUB = N_EPI_WARPS / 8;  // warps sharing one (group, lane quarter): they split the column chunks
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t smem_a = base;
   const uint32_t smem_b = smem_a + p.stages * A_STAGE_BYTES;
-  const uint32_t smem_epi = smem_b + p.stages * p.b_stage_bytes;  // EPI_WARPS x (4 KB + 2 KB), 1024-aligned pieces
-  const uint32_t bars = smem_epi + EPI_WARPS * EPI_BYTES_PER_WARP;
+  const uint32_t smem_epi = smem_b + p.b_region_bytes;  // EPI_WARPS staging regions, 1024-aligned pieces
+  const uint32_t bars = smem_epi + N_EPI_WARPS * p.epi_bytes_per_warp;
   const uint32_t full_bar = bars;                        // MAX_STAGES x 8 B
   const uint32_t empty_bar = bars + 8 * MAX_STAGES;      // MAX_STAGES x 8 B
   const uint32_t tfull_bar = bars + 16 * MAX_STAGES;     // 2 x 8 B
   const uint32_t tempty_bar = tfull_bar + 16;            // 2 x 8 B
   const uint32_t epi_bar = tempty_bar + 16;              // EPI_WARPS x 16 B (residual-load barrier per warp)
-  const uint32_t tmem_slot = epi_bar + 16 * EPI_WARPS;   // 4 B
+  const uint32_t tmem_slot = epi_bar + 16 * EPI_WARPS_MAX;   // 4 B
+  const uint32_t wres_bar = tmem_slot + 8;               // 8 B: resident weight tile landed
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -361,8 +377,12 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const int k_iters = g.n_taps * k_blocks_per_tap;
   const int csz = p.cluster;
   const int cta_rank = csz > 1 ? (int)cluster_cta_rank() : 0;
-  const int unit0 = blockIdx.x / csz, unit_step = gridDim.x / csz;
   const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
+  const bool wres = p.wres != 0;
+  const int unit0 = wres ? blockIdx.x / p.n_tiles_n : blockIdx.x / csz;
+  const int unit_step = wres ? gridDim.x / p.n_tiles_n : gridDim.x / csz;
+  auto tile_m0 = [&](int unit) { return wres ? unit * BLOCK_M : ((unit / p.n_tiles_n) * csz + cta_rank) * BLOCK_M; };
+  auto tile_n0 = [&](int unit) { return wres ? (int)(blockIdx.x % p.n_tiles_n) * p.block_n : (unit % p.n_tiles_n) * p.block_n; };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a0) : "memory");
@@ -376,14 +396,33 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, 128);
+      mbar_init(tempty_bar + 8 * i, 128 * N_SUB);
     }
-    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(epi_bar + 8 * i, 1);
+    for (int i = 0; i < 2 * EPI_WARPS_MAX; ++i) mbar_init(epi_bar + 8 * i, 1);
+    mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {  // per-column vectors -> smem (see TcParams)
+    const int n_fix = wres ? (int)(blockIdx.x % p.n_tiles_n) * p.block_n : 0;
+    float* sm = reinterpret_cast<float*>(smem_raw + (base - raw));
+    for (int i = threadIdx.x; i < p.block_n; i += blockDim.x) {
+      const bool ok = n_fix + i < g.N;
+      if (p.vec_bias) sm[p.vec_bias / 4 + i] = (ok && g.bias) ? g.bias[n_fix + i] : 0.f;
+      if (p.vec_ln1) {
+        sm[p.vec_ln1 / 4 + i] = ok ? g.ln1_gamma[n_fix + i] : 0.f;
+        sm[p.vec_ln1 / 4 + p.block_n + i] = ok ? g.ln1_beta[n_fix + i] : 0.f;
+      }
+      if (p.vec_ln2) {
+        sm[p.vec_ln2 / 4 + i] = ok ? g.ln2_gamma[n_fix + i] : 0.f;
+        sm[p.vec_ln2 / 4 + p.block_n + i] = ok ? g.ln2_beta[n_fix + i] : 0.f;
+      }
+      if (p.vec_act) sm[p.vec_act / 4 + i] = ok ? g.act_vec[n_fix + i] : 1.f;
+      if (p.vec_act2) sm[p.vec_act2 / 4 + i] = ok ? g.act2_vec[n_fix + i] : 1.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -398,17 +437,23 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       uint32_t phase = 0;
       const uint32_t tx_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
       const int b_rows = p.block_n / csz;  // weight rows this CTA fetches (and multicasts)
+      if (wres && unit0 < p.num_units) {   // the whole weight tile of this CTA's n-tile, once
+        mbar_expect_tx(wres_bar, (uint32_t)k_iters * p.block_n * BLOCK_K * 2);
+        for (int it = 0; it < k_iters; ++it)
+          tma_load_2d(&tm.w, wres_bar, smem_b + it * p.b_stage_bytes, it * BLOCK_K, tile_n0(unit0));
+      }
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
-        const int m0 = ((unit / p.n_tiles_n) * csz + cta_rank) * BLOCK_M;
-        const int n0 = (unit % p.n_tiles_n) * p.block_n;
+        const int m0 = tile_m0(unit);
+        const int n0 = tile_n0(unit);
         for (int s = 0; s < g.n_taps; ++s) {
           const CUtensorMap* tmA = g.tap_src[s] ? &tm.a1 : &tm.a0;
           const int arow = m0 + g.tap_shift[s];
           for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
-            mbar_expect_tx(full_bar + 8 * stage, tx_bytes);
+            mbar_expect_tx(full_bar + 8 * stage, wres ? (uint32_t)A_STAGE_BYTES : tx_bytes);
             tma_load_2d(tmA, full_bar + 8 * stage, smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, arow);
-            if (csz == 1)
+            if (wres) {
+            } else if (csz == 1)
               tma_load_2d(&tm.w, full_bar + 8 * stage, smem_b + stage * p.b_stage_bytes, s * g.K_tap + kb * BLOCK_K, n0);
             else
               tma_load_2d_mcast(&tm.w, full_bar + 8 * stage, smem_b + stage * p.b_stage_bytes + cta_rank * b_rows * BLOCK_K * 2,
@@ -428,6 +473,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
+      if (wres && unit0 < p.num_units) mbar_wait(wres_bar, 0, 6);
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2);
         tc_fence_after();
@@ -436,7 +482,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           mbar_wait(full_bar + 8 * stage, phase, 3);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_a + stage * A_STAGE_BYTES);
-          const uint64_t bdesc = make_smem_desc(smem_b + stage * p.b_stage_bytes);
+          const uint64_t bdesc = make_smem_desc(smem_b + (wres ? it : stage) * p.b_stage_bytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 B (= 16 bf16) inside the 128 B swizzle row: +2 in the >>4 address field
@@ -455,25 +501,40 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     // ===================== epilogue: group = accumulator stage =====================
     const int e = warp - 4;
     const int q = e & 3;        // TMEM lane quarter (warp index % 4)
-    const int grp = e >> 2;     // accumulator stage served by this warp
+    const int grp = (e >> 2) & 1;  // accumulator stage served by this warp
+    const int sub_id = e >> 3;     // which share of the column chunks (0 when N_SUB == 1)
     // Staging per warp: R = residual in (TMA load), OF = fp32 out, OB = bf16 out (TMA stores).  R is refilled
     // with chunk c + 1 as soon as every lane has read chunk c, independent of the stores; the output buffers
     // are waited for (cp.async.bulk.wait_group.read) only right before they are rewritten, i.e. after the math.
     // Kernels without fp32 output alternate OF / OB as two bf16 buffers and never wait for the latest store.
-    const uint32_t sR = smem_epi + e * EPI_BYTES_PER_WARP;
-    const uint32_t sOF = sR + EPI_F32_BYTES;
-    const uint32_t sOB = sOF + EPI_F32_BYTES;
+    const uint32_t sR = smem_epi + e * p.epi_bytes_per_warp;
+    const bool small_stage = p.epi_bytes_per_warp <= 2 * EPI_B16_BYTES;  // bf16-only kernels: one or two 2 KB buffers
+    const uint32_t sOF = small_stage ? sR : sR + EPI_F32_BYTES;
+    // kernels without a bf16 copy keep only R + OF (8 KB): the post-LayerNorm sweep then alternates R / OF
+    const uint32_t sOB = small_stage ? (p.epi_bytes_per_warp == EPI_B16_BYTES ? sR : sR + EPI_B16_BYTES)
+                                     : (p.epi_bytes_per_warp == 2 * EPI_F32_BYTES ? sR : sOF + EPI_F32_BYTES);
+    const bool one_buf = small_stage && p.epi_bytes_per_warp == EPI_B16_BYTES;
     const uint32_t ebar = epi_bar + 16 * e;
     uint32_t ephase = 0;
     uint32_t acc_phase = 0;
     const int n_chunks = p.block_n >> 5;
+    const float* smf = reinterpret_cast<const float*>(smem_raw + (base - raw));
     int local_tile = 0;
     for (int unit = unit0; unit < p.num_units; unit += unit_step, ++local_tile) {
       if ((local_tile & 1) != grp) continue;
-      const int m0 = ((unit / p.n_tiles_n) * csz + cta_rank) * BLOCK_M;
-      const int n0 = (unit % p.n_tiles_n) * p.block_n;
+      const int m0 = tile_m0(unit);
+      const int n0 = tile_n0(unit);
       const int row0 = m0 + q * 32;  // first row (view coordinates) of this warp's 32-row slab
+      // per-column vectors, indexed by the absolute column n: smem copy (n-tile fixed per CTA) or global
+      const float* v_bias = g.bias ? (p.vec_bias ? smf + p.vec_bias / 4 - n0 : g.bias) : nullptr;
+      const float* v_g1 = p.vec_ln1 ? smf + p.vec_ln1 / 4 - n0 : g.ln1_gamma;
+      const float* v_b1 = p.vec_ln1 ? smf + p.vec_ln1 / 4 + p.block_n - n0 : g.ln1_beta;
+      const float* v_g2 = p.vec_ln2 ? smf + p.vec_ln2 / 4 - n0 : g.ln2_gamma;
+      const float* v_b2 = p.vec_ln2 ? smf + p.vec_ln2 / 4 + p.block_n - n0 : g.ln2_beta;
+      const float* v_act = g.act_vec ? (p.vec_act ? smf + p.vec_act / 4 - n0 : g.act_vec) : nullptr;
+      const float* v_act2 = g.act2_vec ? (p.vec_act2 ? smf + p.vec_act2 / 4 - n0 : g.act2_vec) : nullptr;
       if (F_RESID && lane == 0) {  // residual of the first chunk: in flight while the accumulator is still being computed
+        if (F_LN2) bulk_wait_read0();  // the previous tile's post-LayerNorm stores may still be reading R
         mbar_expect_tx(ebar, EPI_F32_BYTES);
         tma_load_2d(&tm.resid, ebar, sR, n0, row0);
       }
@@ -497,7 +558,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           tmem_ld32(taddr + c * 32, acc);
           float v[32];
           acc_to_f32(acc, v);
-          if (g.bias) add_vec32(v, g.bias + n0 + c * 32, 32);
+          if (v_bias) add_vec32(v, v_bias + n0 + c * 32, 32);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             s1 += v[j];
@@ -511,16 +572,20 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       // ---- main pass
       float sum2 = 0.f, sq2 = 0.f;
       const int n_chunks_valid = (g.N - n0 + 31) / 32 < n_chunks ? (g.N - n0 + 31) / 32 : n_chunks;
-      for (int c = 0; c < n_chunks_valid; ++c) {
+      for (int c = sub_id; c < ((p.debug & 2) ? 0 : n_chunks_valid); c += N_SUB) {
         const int n = n0 + c * 32;
         const int n_valid = g.N - n < 32 ? g.N - n : 32;
         uint32_t acc[32];
         tmem_ld32(taddr + c * 32, acc);
         float v[32];
         acc_to_f32(acc, v);
-        if (g.bias) add_vec32(v, g.bias + n, n_valid);
-        if (F_LN1) ln_affine32(v, mean1, rstd1, g.ln1_gamma + n, g.ln1_beta + n);
-        if (g.act != ACT_NONE) act32(v, g.act, g.act_param, g.act_vec ? g.act_vec + n : nullptr, n_valid);
+        if (p.debug & 4) {  // experiment: TMEM reads only
+          if (v[0] == 123.456f) printf("x");
+          continue;
+        }
+        if (v_bias && !(p.debug & 8)) add_vec32(v, v_bias + n, n_valid);
+        if (F_LN1) ln_affine32(v, mean1, rstd1, v_g1 + n, v_b1 + n);
+        if (g.act != ACT_NONE) act32(v, g.act, g.act_param, v_act ? v_act + n : nullptr, n_valid);
         if (add_row) add_vec32(v, add_row + n, n_valid);
         if (!row_valid) {
 #pragma unroll
@@ -550,9 +615,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           tmem_st32(taddr + c * 32, acc);
         }
         // output staging: wait (late) for the stores that last used the buffers
-        const uint32_t hbuf = F_F32 ? sOB : ((c & 1) ? sOB : sOF);
+        const uint32_t hbuf = F_F32 ? sOB : (((c / N_SUB) & 1) ? sOB : sOF);
         if (lane == 0) {
-          if (F_F32) bulk_wait_read0();
+          if (F_F32 || one_buf) bulk_wait_read0();
           else bulk_wait_read1();
         }
         __syncwarp();
@@ -561,15 +626,15 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           for (int j = 0; j < 8; ++j) sts128(sOF + swz128(lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (F_OACT) {
-          if (g.act2 != ACT_NONE) act32(v, g.act2, g.act2_param, g.act2_vec ? g.act2_vec + n : nullptr, n_valid);
+          if (g.act2 != ACT_NONE) act32(v, g.act2, g.act2_param, v_act2 ? v_act2 + n : nullptr, n_valid);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128u(hbuf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                     pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         }
-        fence_async_smem();
+        if (!(p.debug & 16)) fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.debug & 1)) {
           if (F_F32) tma_store_2d(&tm.out_f32, sOF, n, row0);
           if (F_OACT) tma_store_2d(&tm.out_act, hbuf, n, row0);
           bulk_commit();
@@ -586,7 +651,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           tmem_ld32(taddr + c * 32, acc);
           float v[32];
           acc_to_f32(acc, v);
-          ln_affine32(v, mean2, rstd2, g.ln2_gamma + n, g.ln2_beta + n);
+          ln_affine32(v, mean2, rstd2, v_g2 + n, v_b2 + n);
           if (!row_valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
