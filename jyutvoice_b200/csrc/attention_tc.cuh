@@ -152,11 +152,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < vc ? __uint_as_float(acc[i]) : -INFINITY);
         }
       }
-      const float m_new = fmaxf(m_run, mx * scale_log2e);
-      const float alpha = fast_exp2(m_run - m_new);  // 0 at j == 0
+      // lazy rescaling: keep the reference max unless the row max grew by more than 2^8 (p <= 256 then: harmless)
+      const float m_tile = mx * scale_log2e;
+      float m_new = m_run, alpha = 1.f;
+      bool rescale = false;
+      if (m_tile > m_run + 8.f) {
+        m_new = m_tile;
+        alpha = fast_exp2(m_run - m_new);  // 0 at j == 0
+        rescale = j > 0;
+      }
+      const bool any_rescale = __any_sync(0xffffffffu, rescale);  // tcgen05.ld / st are warp-collective
       if (j > 0) {
         mbar_wait(bar_o, ph ^ 1, 17);  // O_{j-1} accumulated: O is stable and the P buffer is free
         tc_fence_after();
+      }
+      if (j > 0 && any_rescale) {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t o[32];

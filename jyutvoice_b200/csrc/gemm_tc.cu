@@ -58,7 +58,7 @@ struct KernelEntry {
   int epi;
   KernelFn fn;
 };
-constexpr int N_KERNELS = 8;
+constexpr int N_KERNELS = 9;
 // the epilogue shapes the estimator / HiFT graphs actually use, plus the run-time generic kernel (last)
 static const KernelEntry* kernel_table() {
   using namespace tc;
@@ -70,6 +70,7 @@ static const KernelEntry* kernel_table() {
       {EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>},  // block2 + res + norm1
       {EPI_F32, gemm_taps_tc_kernel<EPI_F32>},                                                // res_conv, final_proj, conv_post
       {EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_RESID | EPI_F32>},                        // HiFT ups + source, last conv2
+      {EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_F32 | EPI_OACT>},                          // HiFT source_downs (im2col)
       {-1, gemm_taps_tc_kernel<-1>},
   };
   return t;

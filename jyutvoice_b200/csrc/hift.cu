@@ -49,7 +49,8 @@ struct jv_hift {
   float *cls_w = nullptr, *cls_b = nullptr, *src_w = nullptr, *src_b = nullptr;
   PackedW conv_pre, conv_post;
   UpW ups[3];
-  PackedW src_down[3];
+  PackedW src_down[3];     // [N, taps*18] for the FFMA path (fp32 mode)
+  PackedW src_down_im[3];  // [N, Kp] zero-padded rows for the im2col + tcgen05 path (bf16 mode)
   ResBlockW src_rb[3], rb[9];
   StftTables stft_tb;
   IstftTables istft_tb;
@@ -148,6 +149,16 @@ static void hift_finalize_impl(jv_hift* h) {
     // source_downs: plain Conv1d(18 -> C, kernel 2u (1 when u == 1), stride u)
     const int su = SRC_U[i], sk = su == 1 ? 1 : 2 * su;
     h->src_down[i] = hpack_conv(h, "source_downs." + std::to_string(i), STAGE_C[i], 18, sk, 18, STAGE_C[i]);
+    {  // same weights as one dense K = Kp row per output channel (tap-major, channel-minor == the im2col window order)
+      const int klen = sk * 18, Kp = round_up(klen, 64);
+      const HostTensor& w = h->store.get("source_downs." + std::to_string(i) + ".weight", {STAGE_C[i], 18, sk});
+      const HostTensor& b = h->store.get("source_downs." + std::to_string(i) + ".bias", {STAGE_C[i]});
+      std::vector<float> wp((size_t)STAGE_C[i] * Kp, 0.f);
+      for (int n = 0; n < STAGE_C[i]; ++n)
+        for (int t = 0; t < sk; ++t)
+          for (int c = 0; c < 18; ++c) wp[(size_t)n * Kp + t * 18 + c] = w.data[((size_t)n * 18 + c) * sk + t];
+      h->src_down_im[i] = hpack(h, std::move(wp), pad_vec(b.data.data(), STAGE_C[i], STAGE_C[i]), STAGE_C[i], Kp, 1);
+    }
     h->src_rb[i] = hpack_resblock(h, "source_resblocks." + std::to_string(i), STAGE_C[i], SRC_K[i]);
     for (int j = 0; j < 3; ++j) h->rb[3 * i + j] = hpack_resblock(h, "resblocks." + std::to_string(3 * i + j), STAGE_C[i], RES_K[j]);
   }
@@ -205,6 +216,7 @@ struct HiftBuffers {
   void *MEL, *H1, *H2;           // f0 predictor
   double* D;                     // source phase prefix [B, 9, Tmax]
   void* SST;                     // [rows2, 18]
+  void* IM;                      // im2col of the source_downs windows (bf16 mode): max over stages of rows * Kp
   void* P[4];                    // conv inputs per level: [Tm,512] [8Tm,256] [40Tm,128] [120Tm,64]
   float* X[3];                   // per stage: x after ups + source fusion (fp32)
   float* S[3][3];                // per stage: the three ResBlock streams (S[i][0] first carries the source branch)
@@ -223,6 +235,12 @@ static HiftBuffers hift_carve(Arena& ar, const Engine& eng, const HiftLayout& L,
   b.H2 = ar.alloc<char>((size_t)L.rows_alloc[0] * 512 * es);
   b.D = ar.alloc<double>((size_t)L.B * 9 * Tmax);
   b.SST = ar.alloc<char>((size_t)L.rows_alloc[3] * 18 * es);
+  {
+    size_t im = 0;
+    const int kp[3] = {576, 128, 64};
+    for (int i = 0; i < 3; ++i) im = std::max(im, (size_t)L.rows_alloc[i + 1] * kp[i] * 2);
+    b.IM = ar.alloc<char>(eng.is_bf16() ? im : 16);
+  }
   const int pc[4] = {512, 256, 128, 64};
   for (int i = 0; i < 4; ++i) b.P[i] = ar.alloc<char>((size_t)L.rows_alloc[i] * pc[i] * es);
   for (int i = 0; i < 3; ++i) {
@@ -411,17 +429,32 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
       const int su = SRC_U[i];
       const PackedW& w = h->src_down[i];
       GemmDesc g = gemm_desc_default();
-      g.A[0] = c.b.SST;
-      g.lda[0] = 18;
-      g.a_rows[0] = c.L.rows_alloc[3];
-      g.a_stride = su;
-      g.n_taps = w.n_taps;
-      g.K_tap = 18;
-      for (int t = 0; t < w.n_taps; ++t) {
-        g.tap_src[t] = 0;
-        g.tap_shift[t] = t - su / 2;
+      if (e.is_bf16()) {  // im2col (a shifted copy) + one dense tcgen05 GEMM
+        const PackedW& wi = h->src_down_im[i];
+        const long rows_out = c.L.rows_alloc[lv_out];
+        const long n = rows_out * (wi.K_tap / 8);
+        hift_im2col_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>((bf16*)c.b.IM, (const bf16*)c.b.SST, rows_out, wi.K_tap,
+                                                                        w.n_taps * 18, su, (long)c.L.rows_alloc[3] * 18);
+        JV_LAUNCHED();
+        g.A[0] = c.b.IM;
+        g.lda[0] = wi.K_tap;
+        g.a_rows[0] = rows_out;
+        g.n_taps = 1;
+        g.K_tap = wi.K_tap;
+        g.W = wi.W;
+      } else {
+        g.A[0] = c.b.SST;
+        g.lda[0] = 18;
+        g.a_rows[0] = c.L.rows_alloc[3];
+        g.a_stride = su;
+        g.n_taps = w.n_taps;
+        g.K_tap = 18;
+        for (int t = 0; t < w.n_taps; ++t) {
+          g.tap_src[t] = 0;
+          g.tap_shift[t] = t - su / 2;
+        }
+        g.W = w.W;
       }
-      g.W = w.W;
       g.M = c.L.rows[lv_out];
       g.N = Cn;
       g.bias = w.bias;
@@ -433,6 +466,7 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
       g.act2 = ACT_SNAKE;
       g.act2_vec = h->src_rb[i].a1[0];
       g.o_rows = c.L.rows_alloc[lv_out];
+      g.algo_flops = 2.0 * (double)c.valid_rows[lv_out] * Cn * w.n_taps * 18;
       e.gemm(g, c.st);
       run_resblock(c, h->src_rb[i], i, c.b.S[i][0], c.b.S[i][0], c.b.XT[i], c.b.XT2[i]);
     }

@@ -177,6 +177,26 @@ __global__ void hift_reflect_fix_kernel(float* __restrict__ X, const float* __re
   X[r0 * Cn + c] = (X[(r0 + 2) * Cn + c] - SI[(r0 + 2) * Cn + c]) + SI[r0 * Cn + c];
 }
 
+// im2col of the strided source_downs convolutions (bf16 mode): IM[m, j] = SST_flat[(m*u - u/2)*18 + j], j < klen,
+// zero beyond; the window of a stride-u, kernel-2u conv over the 18 STFT channels is contiguous in the channel-last
+// layout, so this is a shifted copy.  It turns K_tap = 18 (not TMA-addressable) into one dense K = Kp GEMM.
+__global__ void hift_im2col_kernel(bf16* __restrict__ IM, const bf16* __restrict__ SST, long rows_out, int Kp, int klen, int u,
+                                   long sst_elems) {
+  const int groups = Kp >> 3;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows_out * groups) return;
+  const long m = idx / groups;
+  const int j0 = (int)(idx % groups) * 8;
+  const long base = (m * u - u / 2) * 18 + j0;
+  bf16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long e = base + j;
+    v[j] = (j0 + j < klen && e >= 0 && e < sst_elems) ? SST[e] : __float2bfloat16_rn(0.f);
+  }
+  *reinterpret_cast<uint4*>(IM + m * Kp + j0) = *reinterpret_cast<const uint4*>(v);
+}
+
 // x = (r0 + r1 + r2) / 3 (generator.py:415-421), then the leaky_relu of the next consumer -> conv input
 template <typename TA>
 __global__ void mean3_act_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
