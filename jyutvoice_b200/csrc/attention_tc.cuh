@@ -72,9 +72,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // QKV (previous kernel's output) is read only after this point
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tS = tmem_base, tO = tmem_base + 64;
 
@@ -253,8 +255,19 @@ static inline void launch_attention_tc(TmapCache& cache, const void* qkv, void* 
   const CUtensorMap tm = cache.get(qkv, 1536, M_alloc, 1536 * 2, 64, attn::TQ, 0);
   const CUtensorMap tmkv = cache.get(qkv, 1536, M_alloc, 1536 * 2, 64, attn::TK, 0);
   dim3 grid(cdiv(Tmax_len, attn::TQ), 8, R);
-  attn::attention_tc_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tm, tmkv, (bf16*)out, 512, row_off, row_len,
-                                                                          0.125f * 1.4426950408889634f);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(attn::THREADS);
+  cfg.dynamicSmemBytes = attn::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  lattr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = lattr;
+  cfg.numAttrs = 1;
+  JV_CUDA(cudaLaunchKernelEx(&cfg, attn::attention_tc_kernel, tm, tmkv, (bf16*)out, 512, row_off, row_len,
+                             0.125f * 1.4426950408889634f));
   JV_LAUNCHED();
 }
 

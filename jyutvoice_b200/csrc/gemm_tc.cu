@@ -76,6 +76,15 @@ static const KernelEntry* kernel_table() {
   return t;
 }
 
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool use_wres() {
   static int v = -1;
   if (v < 0) {
@@ -214,13 +223,15 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   cfg.blockDim = dim3(wide ? tc::NUM_THREADS_WIDE : tc::NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: see pdl_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
   KernelFn fn = kernel_table()[N_KERNELS - 1].fn;  // generic
   for (int i = 0; i < N_KERNELS - 1; ++i)
     if (kernel_table()[i].epi == epi) fn = kernel_table()[i].fn;

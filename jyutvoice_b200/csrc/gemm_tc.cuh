@@ -112,6 +112,11 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Programmatic dependent launch: the prologue (barrier init, TMEM allocation, smem vector cache) runs while the
+// previous kernel in the stream drains; nothing produced by that kernel is touched before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -424,10 +429,12 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       if (p.vec_act2) sm[p.vec_act2 / 4 + i] = ok ? g.act2_vec[n_fix + i] : 1.f;
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (csz > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
+  pdl_wait();  // from here on the previous kernel's results (activations, residual stream) may be read / overwritten
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
