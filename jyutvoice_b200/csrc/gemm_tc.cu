@@ -156,7 +156,8 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   int want_bias = (n_fixed && g.bias) ? vbytes : 0, want_ln1 = (n_fixed && g.ln1_gamma) ? 2 * vbytes : 0,
       want_ln2 = (n_fixed && g.ln2_gamma) ? 2 * vbytes : 0, want_act = (n_fixed && g.act_vec) ? vbytes : 0,
       want_act2 = (n_fixed && g.act2_vec) ? vbytes : 0;
-  const int fixed_novec = 1024 + n_epi_warps * p.epi_bytes_per_warp + tc::BAR_BYTES;
+  const int bar_bytes = tc::BAR_BYTES + ((g.ln1_gamma || g.ln2_gamma) ? tc::XCH_BYTES : 0);
+  const int fixed_novec = 1024 + n_epi_warps * p.epi_bytes_per_warp + bar_bytes;
   {
     // smem left after the pipeline the kernel would get WITHOUT any vector cache (never trade a pipeline stage for it)
     int ring = p.wres ? tc::A_STAGE_BYTES : tc::A_STAGE_BYTES + p.b_stage_bytes;
@@ -180,7 +181,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   if (!p.wres) p.b_region_bytes = p.stages * p.b_stage_bytes;
   const int smem = fixed + p.stages * tc::A_STAGE_BYTES + p.b_region_bytes;
   {  // vector cache sits after the barrier block: offsets from the aligned base
-    int off = p.stages * tc::A_STAGE_BYTES + p.b_region_bytes + n_epi_warps * p.epi_bytes_per_warp + tc::BAR_BYTES;
+    int off = p.stages * tc::A_STAGE_BYTES + p.b_region_bytes + n_epi_warps * p.epi_bytes_per_warp + bar_bytes;
     auto place = [&](int want) { int o = want ? off : 0; off += want; return o; };
     p.vec_bias = place(want_bias);
     p.vec_ln1 = place(want_ln1);

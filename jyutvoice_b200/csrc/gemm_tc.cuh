@@ -31,7 +31,8 @@ constexpr int EPI_WARPS_MAX = 16;  // bf16-only epilogues run two warps per (gro
 constexpr int EPI_F32_BYTES = 32 * 32 * 4;  // 4 KB: 32 rows x 128 B, SWIZZLE_128B
 constexpr int EPI_B16_BYTES = 32 * 32 * 2;  // 2 KB: 32 rows x 64 B, SWIZZLE_64B
 constexpr int EPI_BYTES_PER_WARP = 2 * EPI_F32_BYTES + EPI_B16_BYTES;  // residual-in 4 KB | fp32-out 4 KB | bf16-out 2 KB
-constexpr int BAR_BYTES = 512;
+constexpr int BAR_BYTES = 512;   // mbarriers
+constexpr int XCH_BYTES = 2048;  // row-statistics exchange of LayerNorm epilogues: 4 quarters x 2 warps x 32 lanes x float2
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;
@@ -360,7 +361,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const bool F_OACT = EPI >= 0 ? (EPI & EPI_OACT) != 0 : g.out_act != nullptr;
   const bool F_LN2 = EPI >= 0 ? (EPI & EPI_LN2) != 0 : g.ln2_gamma != nullptr;
   constexpr int N_EPI_WARPS = EPI == EPI_OACT ? EPI_WARPS_MAX : EPI_WARPS;
-  constexpr int N_SUB = N_EPI_WARPS / 8;  // warps sharing one (group, lane quarter): they split the column chunks
+  constexpr int N_SUB = N_EPI_WARPS / 4;  // warps sharing one TMEM lane quarter: they split the 32-column chunks of a tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -401,7 +402,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, 128 * N_SUB);
+      mbar_init(tempty_bar + 8 * i, 32 * N_EPI_WARPS);
     }
     for (int i = 0; i < 2 * EPI_WARPS_MAX; ++i) mbar_init(epi_bar + 8 * i, 1);
     mbar_init(wres_bar, 1);
@@ -505,11 +506,30 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: group = accumulator stage =====================
+    // ===================== epilogue: every epilogue warp works on the current tile =====================
+    // Warp e owns TMEM lane quarter q (rows q*32 .. q*32+31 of the tile) and the chunks c == sub_id (mod N_SUB), so a
+    // row is shared by N_SUB threads; LayerNorm statistics are combined through smem + a named barrier per quarter.
+    // A single warp runs this long dependent instruction stream at ~0.2 IPC, so the epilogue latency of a tile scales
+    // with 1 / N_SUB; the accumulator stage alternates per tile, overlapping the next tile's MMAs.
     const int e = warp - 4;
     const int q = e & 3;        // TMEM lane quarter (warp index % 4)
-    const int grp = (e >> 2) & 1;  // accumulator stage served by this warp
-    const int sub_id = e >> 3;     // which share of the column chunks (0 when N_SUB == 1)
+    const int sub_id = e >> 2;  // which share of the column chunks
+    float* xch = reinterpret_cast<float*>(smem_raw + (bars + 512 - raw)) + q * (2 * 32 * 2);  // [2][32][2] for this quarter (LN kernels have N_SUB == 2)
+    auto row_sum2 = [&](float& a, float& b) {  // (a, b) summed over the N_SUB threads that share a row
+      if (N_SUB == 1) return;
+      xch[(sub_id * 32 + lane) * 2] = a;
+      xch[(sub_id * 32 + lane) * 2 + 1] = b;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * N_SUB) : "memory");
+      float ta = 0.f, tb = 0.f;
+#pragma unroll
+      for (int i = 0; i < N_SUB; ++i) {
+        ta += xch[(i * 32 + lane) * 2];
+        tb += xch[(i * 32 + lane) * 2 + 1];
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * N_SUB) : "memory");  // all have read: the slot may be reused
+      a = ta;
+      b = tb;
+    };
     // Staging per warp: R = residual in (TMA load), OF = fp32 out, OB = bf16 out (TMA stores).  R is refilled
     // with chunk c + 1 as soon as every lane has read chunk c, independent of the stores; the output buffers
     // are waited for (cp.async.bulk.wait_group.read) only right before they are rewritten, i.e. after the math.
@@ -524,11 +544,10 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     const uint32_t ebar = epi_bar + 16 * e;
     uint32_t ephase = 0;
     uint32_t acc_phase = 0;
+    int grp = 0;  // accumulator stage of the current tile
     const int n_chunks = p.block_n >> 5;
     const float* smf = reinterpret_cast<const float*>(smem_raw + (base - raw));
-    int local_tile = 0;
-    for (int unit = unit0; unit < p.num_units; unit += unit_step, ++local_tile) {
-      if ((local_tile & 1) != grp) continue;
+    for (int unit = unit0; unit < p.num_units; unit += unit_step) {
       const int m0 = tile_m0(unit);
       const int n0 = tile_n0(unit);
       const int row0 = m0 + q * 32;  // first row (view coordinates) of this warp's 32-row slab
@@ -543,10 +562,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       if (F_RESID && lane == 0) {  // residual of the first chunk: in flight while the accumulator is still being computed
         if (F_LN2) bulk_wait_read0();  // the previous tile's post-LayerNorm stores may still be reading R
         mbar_expect_tx(ebar, EPI_F32_BYTES);
-        tma_load_2d(&tm.resid, ebar, sR, n0, row0);
+        tma_load_2d(&tm.resid, ebar, sR, n0 + sub_id * 32, row0);
       }
       mbar_wait(tfull_bar + 8 * grp, acc_phase, 4);
-      acc_phase ^= 1;
       tc_fence_after();
       const int m = row0 + lane;
       const long orow = (long)m * g.o_stride + g.o_off;
@@ -560,7 +578,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       float mean1 = 0.f, rstd1 = 1.f;
       if (F_LN1) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
         float s1 = 0.f, s2 = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = sub_id; c < n_chunks; c += N_SUB) {
           uint32_t acc[32];
           tmem_ld32(taddr + c * 32, acc);
           float v[32];
@@ -572,6 +590,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             s2 = fmaf(v[j], v[j], s2);
           }
         }
+        row_sum2(s1, s2);
         mean1 = s1 * (1.0f / (float)g.N);
         rstd1 = rsqrtf(fmaxf(s2 * (1.0f / (float)g.N) - mean1 * mean1, 0.f) + 1e-5f);
       }
@@ -607,9 +626,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
           }
           __syncwarp();  // every lane has read R: refill it with the next chunk's residual
-          if (lane == 0 && c + 1 < n_chunks_valid) {
+          if (lane == 0 && c + N_SUB < n_chunks_valid) {
             mbar_expect_tx(ebar, EPI_F32_BYTES);
-            tma_load_2d(&tm.resid, ebar, sR, n + 32, row0);
+            tma_load_2d(&tm.resid, ebar, sR, n + 32 * N_SUB, row0);
           }
         }
         if (F_LN2) {  // keep the final value in TMEM for the post-LayerNorm sweep
@@ -650,9 +669,10 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 
       // ---- optional post-LayerNorm of the final value (norm1 / norm3 of the next transformer block)
       if (F_LN2) {
+        row_sum2(sum2, sq2);
         const float mean2 = sum2 * (1.0f / (float)g.N);
         const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / (float)g.N) - mean2 * mean2, 0.f) + 1e-5f);
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = sub_id; c < n_chunks; c += N_SUB) {
           const int n = n0 + c * 32;
           uint32_t acc[32];
           tmem_ld32(taddr + c * 32, acc);
@@ -664,15 +684,16 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           if (lane == 0) {  // alternate OF / OB as bf16 buffers; the first two chunks wait for the main pass's stores
-            if (c < 2) bulk_wait_read0();
+            if (c < 2 * N_SUB) bulk_wait_read0();
             else bulk_wait_read1();
           }
           __syncwarp();
-          stage_store_b16(&tm.out_ln, (c & 1) ? sOB : sOF, lane, v, n, row0);
+          stage_store_b16(&tm.out_ln, ((c / N_SUB) & 1) ? sOB : sOF, lane, v, n, row0);
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * grp);
+      if (++grp == 2) { grp = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait0();  // smem must outlive the last TMA store's reads
   }
