@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM: tensor-map encoding (driver entry point fetched at run time, so the
 // library does not link libcuda), tile-shape / pipeline-depth choice and launch.
 #include <stdlib.h>
+#include <algorithm>
 
 #include "gemm_tc.cuh"
 
@@ -85,6 +86,25 @@ static bool use_pdl() {
   return v == 1;
 }
 
+// JYUTVOICE_B200_FORCE_MODES=1: use the weight-resident / slab variants even for small problems (parity tests)
+static bool force_modes() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_FORCE_MODES");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+static bool use_slab() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_SLAB");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool use_wres() {
   static int v = -1;
   if (v < 0) {
@@ -140,12 +160,31 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   const int k_iters = (int)(Ktot / tc::BLOCK_K);
   const int epi = (g.ln1_gamma ? tc::EPI_LN1 : 0) | (g.resid ? tc::EPI_RESID : 0) | (g.out_f32 ? tc::EPI_F32 : 0) |
                   (g.out_act ? tc::EPI_OACT : 0) | (g.ln2_gamma ? tc::EPI_LN2 : 0);
-  // weight-resident mode: bf16-only epilogue, whole weight tile <= 128 KB, enough m-tiles per CTA to amortise it
-  const int ctas_per_ntile = num_sms / p.n_tiles_n;
-  p.wres = (epi == tc::EPI_OACT && k_iters * p.b_stage_bytes <= 131072 && ctas_per_ntile >= 1 && m_tiles >= 4 * ctas_per_ntile &&
-            use_wres())
+  // Slab mode (stride-1 conv, one source, resident weights): see TcParams.
+  int min_shift = 0, max_shift = 0;
+  bool one_src = true;
+  for (int t = 0; t < g.n_taps; ++t) {
+    min_shift = t == 0 ? g.tap_shift[t] : std::min(min_shift, g.tap_shift[t]);
+    max_shift = t == 0 ? g.tap_shift[t] : std::max(max_shift, g.tap_shift[t]);
+    if (g.tap_src[t] != 0) one_src = false;
+  }
+  const int slab_rows = round_up(tc::BLOCK_M + (max_shift - min_shift), 8);
+  const bool w_fits = k_iters * p.b_stage_bytes <= 131072;
+  // ... and only if at least two slab stages fit next to the resident weights and the epilogue staging of this kernel
+  const int staging_guess = (epi == tc::EPI_OACT) ? tc::EPI_WARPS_MAX * tc::EPI_B16_BYTES
+                                                  : tc::EPI_WARPS * ((epi & tc::EPI_OACT) ? tc::EPI_BYTES_PER_WARP : 2 * tc::EPI_F32_BYTES);
+  const bool slab_fits = tc::SMEM_LIMIT - (1024 + staging_guess + tc::BAR_BYTES + tc::XCH_BYTES + tc::TAB_BYTES) - k_iters * p.b_stage_bytes >=
+                         2 * round_up(slab_rows * tc::BLOCK_K * 2, 1024);
+  p.slab = (g.n_taps >= 2 && one_src && w_fits && slab_fits && p.n_tiles_n == 1 && slab_rows <= 256 &&
+            (m_tiles >= 4 * num_sms || force_modes()) && use_slab())
                ? 1
                : 0;
+  p.slab_rows = slab_rows;
+  p.min_shift = min_shift;
+  p.a_stage_bytes = p.slab ? round_up(slab_rows * tc::BLOCK_K * 2, 1024) : tc::A_STAGE_BYTES;
+  // weight-resident mode: whole weight tile <= 128 KB, bf16-only epilogue (or slab mode), enough m-tiles per CTA
+  const int ctas_per_ntile = num_sms / p.n_tiles_n;
+  p.wres = (p.slab || (epi == tc::EPI_OACT && w_fits && ctas_per_ntile >= 1 && (m_tiles >= 4 * ctas_per_ntile || force_modes()) && use_wres())) ? 1 : 0;
   const bool wide = epi == tc::EPI_OACT;  // bf16-only epilogue: 16 epilogue warps, small staging
   const int n_epi_warps = wide ? tc::EPI_WARPS_MAX : tc::EPI_WARPS;
   p.epi_bytes_per_warp = wide ? (p.wres ? tc::EPI_B16_BYTES : 2 * tc::EPI_B16_BYTES)
@@ -156,11 +195,12 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   int want_bias = (n_fixed && g.bias) ? vbytes : 0, want_ln1 = (n_fixed && g.ln1_gamma) ? 2 * vbytes : 0,
       want_ln2 = (n_fixed && g.ln2_gamma) ? 2 * vbytes : 0, want_act = (n_fixed && g.act_vec) ? vbytes : 0,
       want_act2 = (n_fixed && g.act2_vec) ? vbytes : 0;
-  const int bar_bytes = tc::BAR_BYTES + ((g.ln1_gamma || g.ln2_gamma) ? tc::XCH_BYTES : 0);
+  const int bar_bytes = tc::BAR_BYTES + ((g.ln1_gamma || g.ln2_gamma) ? tc::XCH_BYTES : 0) + (p.slab ? tc::TAB_BYTES : 0);
+  JV_REQUIRE(!p.slab || g.n_taps * (g.K_tap / tc::BLOCK_K) <= 96, JV_ERR_INVALID, "too many (tap, K block) pairs for slab mode");
   const int fixed_novec = 1024 + n_epi_warps * p.epi_bytes_per_warp + bar_bytes;
+  const int ring = p.wres ? p.a_stage_bytes : p.a_stage_bytes + p.b_stage_bytes;
   {
     // smem left after the pipeline the kernel would get WITHOUT any vector cache (never trade a pipeline stage for it)
-    int ring = p.wres ? tc::A_STAGE_BYTES : tc::A_STAGE_BYTES + p.b_stage_bytes;
     int avail = tc::SMEM_LIMIT - fixed_novec - (p.wres ? k_iters * p.b_stage_bytes : 0);
     int st = avail / ring;
     if (st > tc::MAX_STAGES) st = tc::MAX_STAGES;
@@ -170,18 +210,15 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   }
   const int vec_total = want_bias + want_ln1 + want_ln2 + want_act + want_act2;
   const int fixed = fixed_novec + vec_total;
-  if (p.wres) {
-    p.b_region_bytes = k_iters * p.b_stage_bytes;
-    p.stages = (tc::SMEM_LIMIT - fixed - p.b_region_bytes) / tc::A_STAGE_BYTES;
-  } else {
-    p.stages = (tc::SMEM_LIMIT - fixed) / (tc::A_STAGE_BYTES + p.b_stage_bytes);
-  }
+  p.b_region_bytes = p.wres ? k_iters * p.b_stage_bytes : 0;
+  p.stages = (tc::SMEM_LIMIT - fixed - p.b_region_bytes) / ring;
   if (p.stages > tc::MAX_STAGES) p.stages = tc::MAX_STAGES;
-  JV_REQUIRE(p.stages >= 2, JV_ERR_STATE, "not enough shared memory for the GEMM pipeline");
+  JV_REQUIRE(p.stages >= 2, JV_ERR_STATE, "not enough shared memory for the GEMM pipeline (N=%d K_tap=%d taps=%d epi=%d slab=%d wres=%d fixed=%d bregion=%d ring=%d)", g.N, g.K_tap, g.n_taps, epi, p.slab, p.wres, fixed, p.b_region_bytes, ring);
   if (!p.wres) p.b_region_bytes = p.stages * p.b_stage_bytes;
-  const int smem = fixed + p.stages * tc::A_STAGE_BYTES + p.b_region_bytes;
+  const int smem = fixed + p.stages * p.a_stage_bytes + p.b_region_bytes;
   {  // vector cache sits after the barrier block: offsets from the aligned base
-    int off = p.stages * tc::A_STAGE_BYTES + p.b_region_bytes + n_epi_warps * p.epi_bytes_per_warp + bar_bytes;
+    p.tab_off = p.stages * p.a_stage_bytes + p.b_region_bytes + n_epi_warps * p.epi_bytes_per_warp + bar_bytes - tc::TAB_BYTES;
+    int off = p.stages * p.a_stage_bytes + p.b_region_bytes + n_epi_warps * p.epi_bytes_per_warp + bar_bytes;
     auto place = [&](int want) { int o = want ? off : 0; off += want; return o; };
     p.vec_bias = place(want_bias);
     p.vec_ln1 = place(want_ln1);
@@ -199,7 +236,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   }
   if (cache.maps.size() > 4096) cache.maps.clear();  // before the gets: references must stay valid below
   tc::TcMaps tm;
-  tm.a0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], (long)g.lda[0] * 2, tc::BLOCK_K, tc::BLOCK_M, 0);
+  tm.a0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], (long)g.lda[0] * 2, tc::BLOCK_K, p.slab ? p.slab_rows : tc::BLOCK_M, 0);
   tm.a1 = g.A[1] ? cache.get(g.A[1], g.K_tap, g.a_rows[1], (long)g.lda[1] * 2, tc::BLOCK_K, tc::BLOCK_M, 0) : tm.a0;
   p.cluster = (!p.wres && m_tiles >= 2 && p.block_n % 16 == 0 && use_cluster()) ? 2 : 1;
   p.num_units = p.wres ? m_tiles : cdiv(m_tiles, p.cluster) * p.n_tiles_n;

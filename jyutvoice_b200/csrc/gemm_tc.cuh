@@ -32,6 +32,7 @@ constexpr int EPI_F32_BYTES = 32 * 32 * 4;  // 4 KB: 32 rows x 128 B, SWIZZLE_12
 constexpr int EPI_B16_BYTES = 32 * 32 * 2;  // 2 KB: 32 rows x 64 B, SWIZZLE_64B
 constexpr int EPI_BYTES_PER_WARP = 2 * EPI_F32_BYTES + EPI_B16_BYTES;  // residual-in 4 KB | fp32-out 4 KB | bf16-out 2 KB
 constexpr int BAR_BYTES = 512;   // mbarriers
+constexpr int TAB_BYTES = 1024;  // slab mode: a_off[32] + b_desc[<=96] (uint64)
 constexpr int XCH_BYTES = 2048;  // row-statistics exchange of LayerNorm epilogues: 4 quarters x 2 warps x 32 lanes x float2
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TMEM_COLS = 512;
@@ -305,6 +306,10 @@ struct TcParams {
   // loads its whole weight tile into smem ONCE and streams only activation tiles through the ring.  The kernel is
   // bound by SM <-> L2 traffic, and the weight tile is 2/3 of a 128 x 256 tile's operand bytes.
   int wres;
+  // Slab mode (implies wres; stride-1 convs, one activation source): per 64-channel K block ONE activation slab of
+  // 128 + (max_shift - min_shift) rows is loaded, and every tap multiplies a row-shifted view of it (descriptor start address) with its resident weight tile.  A conv tap then costs no activation traffic at all.
+  int slab, slab_rows, min_shift, a_stage_bytes;
+  int tab_off;  // slab mode: smem offset of the per-tap descriptor tables (the MMA thread must issue one MMA per ~32 cycles)
   int b_region_bytes;      // ring: stages * b_stage_bytes; resident: k_iters * b_stage_bytes
   int epi_bytes_per_warp;  // 10 KB (residual + fp32 + bf16 staging) or 4 KB (two bf16 buffers)
   // Per-column vectors cached in smem once per CTA (byte offsets from the aligned smem base; 0 = read from global).
@@ -366,7 +371,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t smem_a = base;
-  const uint32_t smem_b = smem_a + p.stages * A_STAGE_BYTES;
+  const uint32_t smem_b = smem_a + p.stages * p.a_stage_bytes;
   const uint32_t smem_epi = smem_b + p.b_region_bytes;  // EPI_WARPS staging regions, 1024-aligned pieces
   const uint32_t bars = smem_epi + N_EPI_WARPS * p.epi_bytes_per_warp;
   const uint32_t full_bar = bars;                        // MAX_STAGES x 8 B
@@ -412,6 +417,16 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (p.slab && warp == 3) {  // descriptor tables for the MMA thread: everything that does not depend on the ring stage
+    uint64_t* tab = reinterpret_cast<uint64_t*>(smem_raw + (base - raw) + p.tab_off);
+    for (int s2 = lane; s2 < g.n_taps; s2 += 32) {
+      const uint32_t d = (uint32_t)(g.tap_shift[s2] - p.min_shift);
+      // start address += d rows (128 B = 8 x 16 B).  No descriptor base offset: measured on B200, the tensor core applies the
+      // 128B swizzle to the absolute smem address, exactly as TMA wrote the slab, so a row-shifted view needs nothing else.
+      tab[s2] = (uint64_t)(d * 8u);
+    }
+    for (int i = lane; i < g.n_taps * k_blocks_per_tap; i += 32) tab[32 + i] = make_smem_desc(smem_b + i * p.b_stage_bytes);
+  }
   {  // per-column vectors -> smem (see TcParams)
     const int n_fix = wres ? (int)(blockIdx.x % p.n_tiles_n) * p.block_n : 0;
     float* sm = reinterpret_cast<float*>(smem_raw + (base - raw));
@@ -444,6 +459,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+      const bool slab = p.slab != 0;
       const int b_rows = p.block_n / csz;  // weight rows this CTA fetches (and multicasts)
       if (wres && unit0 < p.num_units) {   // the whole weight tile of this CTA's n-tile, once
         mbar_expect_tx(wres_bar, (uint32_t)k_iters * p.block_n * BLOCK_K * 2);
@@ -453,13 +469,22 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         const int m0 = tile_m0(unit);
         const int n0 = tile_n0(unit);
+        if (slab) {  // one slab per 64-channel block, shared by all taps
+          for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
+            mbar_expect_tx(full_bar + 8 * stage, (uint32_t)p.slab_rows * BLOCK_K * 2);
+            tma_load_2d(&tm.a0, full_bar + 8 * stage, smem_a + stage * p.a_stage_bytes, kb * BLOCK_K, m0 + p.min_shift);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int s = 0; s < g.n_taps; ++s) {
           const CUtensorMap* tmA = g.tap_src[s] ? &tm.a1 : &tm.a0;
           const int arow = m0 + g.tap_shift[s];
           for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
             mbar_expect_tx(full_bar + 8 * stage, wres ? (uint32_t)A_STAGE_BYTES : tx_bytes);
-            tma_load_2d(tmA, full_bar + 8 * stage, smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, arow);
+            tma_load_2d(tmA, full_bar + 8 * stage, smem_a + stage * p.a_stage_bytes, kb * BLOCK_K, arow);
             if (wres) {
             } else if (csz == 1)
               tma_load_2d(&tm.w, full_bar + 8 * stage, smem_b + stage * p.b_stage_bytes, s * g.K_tap + kb * BLOCK_K, n0);
@@ -486,10 +511,30 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_stage * 256;
+        if (p.slab) {
+          const uint64_t* tab = reinterpret_cast<const uint64_t*>(smem_raw + (base - raw) + p.tab_off);
+          for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
+            mbar_wait(full_bar + 8 * stage, phase, 3);
+            tc_fence_after();
+            const uint64_t a_stage_desc = make_smem_desc(smem_a + stage * p.a_stage_bytes);  // 1024-aligned: base offset 0
+            for (int s = 0; s < g.n_taps; ++s) {
+              const uint64_t adesc = a_stage_desc + tab[s];
+              const uint64_t bdesc = tab[32 + s * k_blocks_per_tap + kb];
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || s > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar + 8 * stage);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(tfull_bar + 8 * acc_stage);
+          if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+          continue;
+        }
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(full_bar + 8 * stage, phase, 3);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_a + stage * A_STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(smem_a + stage * p.a_stage_bytes);
           const uint64_t bdesc = make_smem_desc(smem_b + (wres ? it : stage) * p.b_stage_bytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {

@@ -215,7 +215,9 @@ def test_hift_full_size_properties(hifts):
     assert torch.equal(wav, wav2)
     assert torch.isfinite(wav).all() and float(wav.abs().max()) <= 0.99 + 1e-6
     one, _ = hift.inference(mel[5:6], rng={"phase": rng["phase"][5:6], "noise": rng["noise"][5:6]})
-    assert torch.equal(one[0], wav[5])
+    # not bit-equal by design: large batches run the convs in slab mode (K blocks outer, taps inner), small ones tap-major,
+    # so the fp32 accumulation order differs; the utterance itself must not depend on its neighbours beyond that
+    assert snr_db(one[0], wav[5]) >= 55.0
 
 
 def test_inference_draws_rng_like_the_reference(hifts):
