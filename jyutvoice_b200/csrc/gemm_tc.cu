@@ -96,6 +96,15 @@ static bool force_modes() {
   return v == 1;
 }
 
+static bool use_tile_par() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_TILEPAR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool use_slab() {
   static int v = -1;
   if (v < 0) {
@@ -195,6 +204,15 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   int want_bias = (n_fixed && g.bias) ? vbytes : 0, want_ln1 = (n_fixed && g.ln1_gamma) ? 2 * vbytes : 0,
       want_ln2 = (n_fixed && g.ln2_gamma) ? 2 * vbytes : 0, want_act = (n_fixed && g.act_vec) ? vbytes : 0,
       want_act2 = (n_fixed && g.act2_vec) ? vbytes : 0;
+  {
+    const int n_sub = n_epi_warps / 4;
+    const int n_chunks = p.block_n / 32;
+    p.acc_cols = p.block_n;
+    p.n_acc = std::min(tc::MAX_ACC, tc::TMEM_COLS / p.block_n);
+    // tile-parallel epilogue for narrow tiles without LayerNorm (row statistics need the chunk split)
+    p.tile_par = (n_chunks < 2 * n_sub && !g.ln1_gamma && !g.ln2_gamma && p.n_acc >= n_sub && use_tile_par()) ? 1 : 0;
+    if (!p.tile_par) p.n_acc = 2;
+  }
   const int bar_bytes = tc::BAR_BYTES + ((g.ln1_gamma || g.ln2_gamma) ? tc::XCH_BYTES : 0) + (p.slab ? tc::TAB_BYTES : 0);
   JV_REQUIRE(!p.slab || g.n_taps * (g.K_tap / tc::BLOCK_K) <= 96, JV_ERR_INVALID, "too many (tap, K block) pairs for slab mode");
   const int fixed_novec = 1024 + n_epi_warps * p.epi_bytes_per_warp + bar_bytes;

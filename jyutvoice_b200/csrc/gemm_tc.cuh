@@ -31,7 +31,8 @@ constexpr int EPI_WARPS_MAX = 16;  // bf16-only epilogues run two warps per (gro
 constexpr int EPI_F32_BYTES = 32 * 32 * 4;  // 4 KB: 32 rows x 128 B, SWIZZLE_128B
 constexpr int EPI_B16_BYTES = 32 * 32 * 2;  // 2 KB: 32 rows x 64 B, SWIZZLE_64B
 constexpr int EPI_BYTES_PER_WARP = 2 * EPI_F32_BYTES + EPI_B16_BYTES;  // residual-in 4 KB | fp32-out 4 KB | bf16-out 2 KB
-constexpr int BAR_BYTES = 512;   // mbarriers
+constexpr int BAR_BYTES = 640;   // mbarriers
+constexpr int MAX_ACC = 8;       // accumulator stages in TMEM (512 columns / block_n, at most 8)
 constexpr int TAB_BYTES = 1024;  // slab mode: a_off[32] + b_desc[<=96] (uint64)
 constexpr int XCH_BYTES = 2048;  // row-statistics exchange of LayerNorm epilogues: 4 quarters x 2 warps x 32 lanes x float2
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -309,6 +310,10 @@ struct TcParams {
   // Slab mode (implies wres; stride-1 convs, one activation source): per 64-channel K block ONE activation slab of
   // 128 + (max_shift - min_shift) rows is loaded, and every tap multiplies a row-shifted view of it (descriptor start address) with its resident weight tile.  A conv tap then costs no activation traffic at all.
   int slab, slab_rows, min_shift, a_stage_bytes;
+  // Accumulator stages in TMEM: 512 / block_n (2 for N = 256 ... 8 for N <= 64).  Tile-parallel epilogue: with few
+  // 32-column chunks per tile (narrow N) each share of the epilogue warps takes whole tiles (tile t -> share t % N_SUB)
+  // instead of splitting one tile's chunks, so several tiles are in flight and the per-tile TMA round trips overlap.
+  int n_acc, acc_cols, tile_par;
   int tab_off;  // slab mode: smem offset of the per-tap descriptor tables (the MMA thread must issue one MMA per ~32 cycles)
   int b_region_bytes;      // ring: stages * b_stage_bytes; resident: k_iters * b_stage_bytes
   int epi_bytes_per_warp;  // 10 KB (residual + fp32 + bf16 staging) or 4 KB (two bf16 buffers)
@@ -376,9 +381,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const uint32_t bars = smem_epi + N_EPI_WARPS * p.epi_bytes_per_warp;
   const uint32_t full_bar = bars;                        // MAX_STAGES x 8 B
   const uint32_t empty_bar = bars + 8 * MAX_STAGES;      // MAX_STAGES x 8 B
-  const uint32_t tfull_bar = bars + 16 * MAX_STAGES;     // 2 x 8 B
-  const uint32_t tempty_bar = tfull_bar + 16;            // 2 x 8 B
-  const uint32_t epi_bar = tempty_bar + 16;              // EPI_WARPS x 16 B (residual-load barrier per warp)
+  const uint32_t tfull_bar = bars + 16 * MAX_STAGES;     // MAX_ACC x 8 B
+  const uint32_t tempty_bar = tfull_bar + 8 * MAX_ACC;   // MAX_ACC x 8 B
+  const uint32_t epi_bar = tempty_bar + 8 * MAX_ACC;     // EPI_WARPS_MAX x 16 B (residual-load barrier per warp)
   const uint32_t tmem_slot = epi_bar + 16 * EPI_WARPS_MAX;   // 4 B
   const uint32_t wres_bar = tmem_slot + 8;               // 8 B: resident weight tile landed
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
@@ -405,9 +410,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       mbar_init(full_bar + 8 * i, 1);
       mbar_init(empty_bar + 8 * i, csz);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < p.n_acc; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, 32 * N_EPI_WARPS);
+      mbar_init(tempty_bar + 8 * i, p.tile_par ? 128 : 32 * N_EPI_WARPS);
     }
     for (int i = 0; i < 2 * EPI_WARPS_MAX; ++i) mbar_init(epi_bar + 8 * i, 1);
     mbar_init(wres_bar, 1);
@@ -510,7 +515,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc_stage * 256;
+        const uint32_t d_tmem = tmem_base + acc_stage * p.acc_cols;
         if (p.slab) {
           const uint64_t* tab = reinterpret_cast<const uint64_t*>(smem_raw + (base - raw) + p.tab_off);
           for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
@@ -528,7 +533,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
           umma_commit(tfull_bar + 8 * acc_stage);
-          if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+          if (++acc_stage == p.n_acc) { acc_stage = 0; acc_phase ^= 1; }
           continue;
         }
         for (int it = 0; it < k_iters; ++it) {
@@ -547,7 +552,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull_bar + 8 * acc_stage);  // accumulator complete -> epilogue
-        if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+        if (++acc_stage == p.n_acc) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -590,9 +595,17 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     uint32_t ephase = 0;
     uint32_t acc_phase = 0;
     int grp = 0;  // accumulator stage of the current tile
+    const bool tile_par = p.tile_par != 0;
+    const int c_first = tile_par ? 0 : sub_id, c_step = tile_par ? 1 : N_SUB;
+    int t_local = 0;   // tiles seen by this CTA
+    uint32_t n_out = 0;  // output chunks staged by this warp (alternates the bf16 staging buffers)
     const int n_chunks = p.block_n >> 5;
     const float* smf = reinterpret_cast<const float*>(smem_raw + (base - raw));
-    for (int unit = unit0; unit < p.num_units; unit += unit_step) {
+    for (int unit = unit0; unit < p.num_units; unit += unit_step, ++t_local) {
+      if (tile_par && (t_local % N_SUB) != sub_id) {  // another share's tile: just keep the stage / phase counters in step
+        if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
+        continue;
+      }
       const int m0 = tile_m0(unit);
       const int n0 = tile_n0(unit);
       const int row0 = m0 + q * 32;  // first row (view coordinates) of this warp's 32-row slab
@@ -607,7 +620,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       if (F_RESID && lane == 0) {  // residual of the first chunk: in flight while the accumulator is still being computed
         if (F_LN2) bulk_wait_read0();  // the previous tile's post-LayerNorm stores may still be reading R
         mbar_expect_tx(ebar, EPI_F32_BYTES);
-        tma_load_2d(&tm.resid, ebar, sR, n0 + sub_id * 32, row0);
+        tma_load_2d(&tm.resid, ebar, sR, n0 + c_first * 32, row0);
       }
       mbar_wait(tfull_bar + 8 * grp, acc_phase, 4);
       tc_fence_after();
@@ -616,14 +629,14 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const bool in_range = m < g.M && orow < g.o_rows;
       const int fr = (in_range && g.frame_row) ? g.frame_row[orow] : (in_range ? 0 : -1);
       const bool row_valid = fr >= 0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * p.acc_cols;
       const float* add_row = (F_LN1 && g.add_row && row_valid) ? g.add_row + (long)g.row_tidx[fr] * g.add_row_stride : nullptr;
 
       // ---- optional pre-LayerNorm statistics of (acc + bias) over the whole row (block_n == N == 256)
       float mean1 = 0.f, rstd1 = 1.f;
       if (F_LN1) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
         float s1 = 0.f, s2 = 0.f;
-        for (int c = sub_id; c < n_chunks; c += N_SUB) {
+        for (int c = c_first; c < n_chunks; c += c_step) {
           uint32_t acc[32];
           tmem_ld32(taddr + c * 32, acc);
           float v[32];
@@ -635,7 +648,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             s2 = fmaf(v[j], v[j], s2);
           }
         }
-        row_sum2(s1, s2);
+        if (!tile_par) row_sum2(s1, s2);
         mean1 = s1 * (1.0f / (float)g.N);
         rstd1 = rsqrtf(fmaxf(s2 * (1.0f / (float)g.N) - mean1 * mean1, 0.f) + 1e-5f);
       }
@@ -643,7 +656,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       // ---- main pass
       float sum2 = 0.f, sq2 = 0.f;
       const int n_chunks_valid = (g.N - n0 + 31) / 32 < n_chunks ? (g.N - n0 + 31) / 32 : n_chunks;
-      for (int c = sub_id; c < ((p.debug & 2) ? 0 : n_chunks_valid); c += N_SUB) {
+      for (int c = c_first; c < ((p.debug & 2) ? 0 : n_chunks_valid); c += c_step) {
         const int n = n0 + c * 32;
         const int n_valid = g.N - n < 32 ? g.N - n : 32;
         uint32_t acc[32];
@@ -671,9 +684,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
           }
           __syncwarp();  // every lane has read R: refill it with the next chunk's residual
-          if (lane == 0 && c + N_SUB < n_chunks_valid) {
+          if (lane == 0 && c + c_step < n_chunks_valid) {
             mbar_expect_tx(ebar, EPI_F32_BYTES);
-            tma_load_2d(&tm.resid, ebar, sR, n + 32 * N_SUB, row0);
+            tma_load_2d(&tm.resid, ebar, sR, n + 32 * c_step, row0);
           }
         }
         if (F_LN2) {  // keep the final value in TMEM for the post-LayerNorm sweep
@@ -686,7 +699,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           tmem_st32(taddr + c * 32, acc);
         }
         // output staging: wait (late) for the stores that last used the buffers
-        const uint32_t hbuf = F_F32 ? sOB : (((c / N_SUB) & 1) ? sOB : sOF);
+        const uint32_t hbuf = F_F32 ? sOB : ((n_out & 1) ? sOB : sOF);
+        ++n_out;
         if (lane == 0) {
           if (F_F32 || one_buf) bulk_wait_read0();
           else bulk_wait_read1();
@@ -714,10 +728,11 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 
       // ---- optional post-LayerNorm of the final value (norm1 / norm3 of the next transformer block)
       if (F_LN2) {
-        row_sum2(sum2, sq2);
+        if (!tile_par) row_sum2(sum2, sq2);
         const float mean2 = sum2 * (1.0f / (float)g.N);
         const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / (float)g.N) - mean2 * mean2, 0.f) + 1e-5f);
-        for (int c = sub_id; c < n_chunks; c += N_SUB) {
+        int n_ln = 0;
+        for (int c = c_first; c < n_chunks; c += c_step, ++n_ln) {
           const int n = n0 + c * 32;
           uint32_t acc[32];
           tmem_ld32(taddr + c * 32, acc);
@@ -729,16 +744,16 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           if (lane == 0) {  // alternate OF / OB as bf16 buffers; the first two chunks wait for the main pass's stores
-            if (c < 2 * N_SUB) bulk_wait_read0();
+            if (n_ln < 2) bulk_wait_read0();
             else bulk_wait_read1();
           }
           __syncwarp();
-          stage_store_b16(&tm.out_ln, ((c / N_SUB) & 1) ? sOB : sOF, lane, v, n, row0);
+          stage_store_b16(&tm.out_ln, (n_ln & 1) ? sOB : sOF, lane, v, n, row0);
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * grp);
-      if (++grp == 2) { grp = 0; acc_phase ^= 1; }
+      if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait0();  // smem must outlive the last TMA store's reads
   }
