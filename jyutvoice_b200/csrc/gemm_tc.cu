@@ -180,8 +180,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   const int slab_rows = round_up(tc::BLOCK_M + (max_shift - min_shift), 8);
   const bool w_fits = k_iters * p.b_stage_bytes <= 131072;
   // ... and only if at least two slab stages fit next to the resident weights and the epilogue staging of this kernel
-  const int staging_guess = (epi == tc::EPI_OACT) ? tc::EPI_WARPS_MAX * tc::EPI_B16_BYTES
-                                                  : tc::EPI_WARPS * ((epi & tc::EPI_OACT) ? tc::EPI_BYTES_PER_WARP : 2 * tc::EPI_F32_BYTES);
+  const int staging_guess = (epi == tc::EPI_OACT) ? tc::EPI_WARPS_MAX * tc::EPI_B16_BYTES : tc::EPI_WARPS * tc::EPI_BYTES_PER_WARP;
   const bool slab_fits = tc::SMEM_LIMIT - (1024 + staging_guess + tc::BAR_BYTES + tc::XCH_BYTES + tc::TAB_BYTES) - k_iters * p.b_stage_bytes >=
                          2 * round_up(slab_rows * tc::BLOCK_K * 2, 1024);
   p.slab = (g.n_taps >= 2 && one_src && w_fits && slab_fits && p.n_tiles_n == 1 && slab_rows <= 256 &&
@@ -196,8 +195,24 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   p.wres = (p.slab || (epi == tc::EPI_OACT && w_fits && ctas_per_ntile >= 1 && (m_tiles >= 4 * ctas_per_ntile || force_modes()) && use_wres())) ? 1 : 0;
   const bool wide = epi == tc::EPI_OACT;  // bf16-only epilogue: 16 epilogue warps, small staging
   const int n_epi_warps = wide ? tc::EPI_WARPS_MAX : tc::EPI_WARPS;
-  p.epi_bytes_per_warp = wide ? (p.wres ? tc::EPI_B16_BYTES : 2 * tc::EPI_B16_BYTES)
-                              : ((epi & tc::EPI_OACT) ? tc::EPI_BYTES_PER_WARP : 2 * tc::EPI_F32_BYTES);
+  {  // staging layout per epilogue warp, exactly what this epilogue kind needs
+    const bool f_resid = epi & tc::EPI_RESID, f_f32 = epi & tc::EPI_F32, f_oact = epi & tc::EPI_OACT;
+    int off = 0;
+    p.off_R = 0;
+    if (f_resid) off += tc::EPI_F32_BYTES;
+    p.off_OF = off;
+    if (f_f32) {
+      off += tc::EPI_F32_BYTES;
+      p.off_OB = f_oact ? off : p.off_R;       // bf16 copy next to the fp32 buffer, or (LN2 only) alternate with R
+      if (f_oact) off += tc::EPI_B16_BYTES;
+      if (!f_oact && !f_resid) { p.off_OB = off; off += tc::EPI_B16_BYTES; }  // fp32-only kernel with an LN2 output (unused today)
+    } else {                                   // bf16 outputs only: two buffers (one in weight-resident wide kernels: smem is tight)
+      off += tc::EPI_B16_BYTES;
+      if (wide && p.wres) p.off_OB = p.off_OF;
+      else { p.off_OB = off; off += tc::EPI_B16_BYTES; }
+    }
+    p.epi_bytes_per_warp = round_up(off, 1024);
+  }
   // per-column vector cache (only when the CTA's n-tile is fixed), in priority order while smem remains
   const bool n_fixed = p.n_tiles_n == 1 || p.wres;
   const int vbytes = p.block_n * 4;

@@ -316,7 +316,8 @@ struct TcParams {
   int n_acc, acc_cols, tile_par;
   int tab_off;  // slab mode: smem offset of the per-tap descriptor tables (the MMA thread must issue one MMA per ~32 cycles)
   int b_region_bytes;      // ring: stages * b_stage_bytes; resident: k_iters * b_stage_bytes
-  int epi_bytes_per_warp;  // 10 KB (residual + fp32 + bf16 staging) or 4 KB (two bf16 buffers)
+  int epi_bytes_per_warp;  // staging per epilogue warp; pieces at off_R (residual in, 4 KB), off_OF (fp32 out, 4 KB or the
+  int off_R, off_OF, off_OB;  // first bf16 buffer), off_OB (second bf16 buffer, 2 KB); equal offsets = shared / single buffer
   // Per-column vectors cached in smem once per CTA (byte offsets from the aligned smem base; 0 = read from global).
   // Only when the CTA's n-tile is fixed (one n-tile, or weight-resident mode).  With 227 KB of smem there is no L1,
   // so every uncached read of bias / gamma / beta / alpha is an L2 round trip inside the epilogue's dependency chain.
@@ -584,13 +585,10 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     // with chunk c + 1 as soon as every lane has read chunk c, independent of the stores; the output buffers
     // are waited for (cp.async.bulk.wait_group.read) only right before they are rewritten, i.e. after the math.
     // Kernels without fp32 output alternate OF / OB as two bf16 buffers and never wait for the latest store.
-    const uint32_t sR = smem_epi + e * p.epi_bytes_per_warp;
-    const bool small_stage = p.epi_bytes_per_warp <= 2 * EPI_B16_BYTES;  // bf16-only kernels: one or two 2 KB buffers
-    const uint32_t sOF = small_stage ? sR : sR + EPI_F32_BYTES;
-    // kernels without a bf16 copy keep only R + OF (8 KB): the post-LayerNorm sweep then alternates R / OF
-    const uint32_t sOB = small_stage ? (p.epi_bytes_per_warp == EPI_B16_BYTES ? sR : sR + EPI_B16_BYTES)
-                                     : (p.epi_bytes_per_warp == 2 * EPI_F32_BYTES ? sR : sOF + EPI_F32_BYTES);
-    const bool one_buf = small_stage && p.epi_bytes_per_warp == EPI_B16_BYTES;
+    const uint32_t sR = smem_epi + e * p.epi_bytes_per_warp + p.off_R;
+    const uint32_t sOF = smem_epi + e * p.epi_bytes_per_warp + p.off_OF;
+    const uint32_t sOB = smem_epi + e * p.epi_bytes_per_warp + p.off_OB;  // kernels without a bf16 copy: == sR (LN2 sweep alternates R / OF)
+    const bool one_buf = p.off_OB == p.off_OF;                            // a single bf16 staging buffer
     const uint32_t ebar = epi_bar + 16 * e;
     uint32_t ephase = 0;
     uint32_t acc_phase = 0;
