@@ -173,41 +173,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// ---------------------------------------------------------------- fast epilogue math (bf16 mode only:
-// results are rounded to bf16 or feed bf16 operands, so ~1e-6 absolute error is invisible)
-__device__ __forceinline__ float fast_erf(float x) {
-  // Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float r = 1.0f - p * t * __expf(-ax * ax);
-  return copysignf(r, x);
-}
-__device__ __forceinline__ float fast_mish(float x) {
-  // x * tanh(softplus(x)) = x * (e^2 + 2e) / (e^2 + 2e + 2), e = exp(x)
-  if (x > 20.f) return x;
-  const float e = __expf(x);
-  const float n = e * (e + 2.0f);
-  return x * __fdividef(n, n + 2.0f);
-}
-__device__ __forceinline__ float apply_act_fast(float v, int act, float p, float a) {
-  switch (act) {
-    case ACT_GELU: return 0.5f * v * (1.f + fast_erf(v * 0.70710678118654752440f));
-    case ACT_ELU: return v > 0.f ? v : __expf(v) - 1.0f;
-    case ACT_LRELU: return v > 0.f ? v : v * p;
-    case ACT_SNAKE: {
-      const float s = __sinf(v * a);
-      return fmaf(__frcp_rn(a + 1e-9f) * s, s, v);
-    }
-    case ACT_MISH: return fast_mish(v);
-    case ACT_SILU: return __fdividef(v, 1.f + __expf(-v));
-    default: return v;
-  }
-}
-
 // ---------------------------------------------------------------- row-chunk helpers: 32 consecutive columns of one row per thread.
 // Every optional epilogue step is its own unswitched loop over the 32 registers, so a feature that is off costs one
 // uniform branch per chunk instead of one per element.  Per-column vectors are read as float4 (same address in every
@@ -252,11 +217,11 @@ __device__ __forceinline__ void act32(float (&v)[32], int act, float prm, const 
       break;
     case ACT_ELU:
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : __expf(v[j]) - 1.0f;
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + (exp_fast(fminf(v[j], 0.f)) - 1.0f);
       break;
     case ACT_LRELU:
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * prm;
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + prm * fminf(v[j], 0.f);
       break;
     case ACT_MISH:
 #pragma unroll
@@ -264,7 +229,7 @@ __device__ __forceinline__ void act32(float (&v)[32], int act, float prm, const 
       break;
     case ACT_SILU:
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+      for (int j = 0; j < 32; ++j) v[j] = v[j] * rcp_ftz(1.f + exp_fast(-v[j]));
       break;
     case ACT_SNAKE:
 #pragma unroll
@@ -275,8 +240,8 @@ __device__ __forceinline__ void act32(float (&v)[32], int act, float prm, const 
           const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float sn = __sinf(v[j8 * 8 + j] * al[j]);
-            v[j8 * 8 + j] = fmaf(__frcp_rn(al[j] + 1e-9f) * sn, sn, v[j8 * 8 + j]);
+            const float sn = sin_ftz(v[j8 * 8 + j] * al[j]);
+            v[j8 * 8 + j] = fmaf(rcp_ftz(al[j] + 1e-9f) * sn, sn, v[j8 * 8 + j]);
           }
         }
       }
@@ -459,6 +424,10 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   pdl_wait();  // from here on the previous kernel's results (activations, residual stream) may be read / overwritten
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Register re-partitioning (general kernels, 384 threads): the producer / MMA / allocator warpgroup keeps 40 registers,
+  // the two epilogue warpgroups grow to 232, which lets the compiler interleave the 32 independent element chains of a chunk.
+  if (warp < 4) {
+  if (N_EPI_WARPS == EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -556,7 +525,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         if (++acc_stage == p.n_acc) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    if (N_EPI_WARPS == EPI_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ===================== epilogue: every epilogue warp works on the current tile =====================
     // Warp e owns TMEM lane quarter q (rows q*32 .. q*32+31 of the tile) and the chunks c == sub_id (mod N_SUB), so a
     // row is shared by N_SUB threads; LayerNorm statistics are combined through smem + a named barrier per quarter.
@@ -632,7 +603,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 
       // ---- optional pre-LayerNorm statistics of (acc + bias) over the whole row (block_n == N == 256)
       float mean1 = 0.f, rstd1 = 1.f;
-      if (F_LN1) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
+      if (F_LN1 && !(p.debug & 32)) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
         float s1 = 0.f, s2 = 0.f;
         for (int c = c_first; c < n_chunks; c += c_step) {
           uint32_t acc[32];
@@ -666,8 +637,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           continue;
         }
         if (v_bias && !(p.debug & 8)) add_vec32(v, v_bias + n, n_valid);
-        if (F_LN1) ln_affine32(v, mean1, rstd1, v_g1 + n, v_b1 + n);
-        if (g.act != ACT_NONE) act32(v, g.act, g.act_param, v_act ? v_act + n : nullptr, n_valid);
+        if (F_LN1 && !(p.debug & 128)) ln_affine32(v, mean1, rstd1, v_g1 + n, v_b1 + n);
+        if (g.act != ACT_NONE && !(p.debug & 64)) act32(v, g.act, g.act_param, v_act ? v_act + n : nullptr, n_valid);
         if (add_row) add_vec32(v, add_row + n, n_valid);
         if (!row_valid) {
 #pragma unroll

@@ -162,7 +162,10 @@ __global__ void act_rows_kernel(const float* __restrict__ in, TA* __restrict__ o
   const int c = (int)(i % Cn);
   float r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) r[j] = apply_act(r[j], act, p, vec ? __ldg(vec + c + j) : 0.f);
+  for (int j = 0; j < 4; ++j) {
+    const float a = vec ? __ldg(vec + c + j) : 0.f;
+    r[j] = sizeof(TA) == 2 ? apply_act_fast(r[j], act, p, a) : apply_act(r[j], act, p, a);  // bf16 mode: single-MUFU forms
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) out[i + j] = DT<TA>::from_f(r[j]);
 }
