@@ -80,6 +80,7 @@ int jv_bench_gemm(int M, int N, int K_tap, int taps, int mode, int iters, double
   if (mode & 4) { g.ln1_gamma = vec; g.ln1_beta = vec; g.act = ACT_MISH; }
   if (mode & 8) { g.ln2_gamma = vec; g.ln2_beta = vec; g.out_ln = OL; g.ldo3 = N; }
   if (mode & 16) { g.out_act = OA; g.ldo2 = N; }
+  if (mode & 32) g.x_bf16 = 1;  // R / OF buffers are simply over-allocated
   JV_REQUIRE(gemm_tc_supported(g), JV_ERR_INVALID, "shape not supported by the tcgen05 engine");
   cudaEvent_t e0, e1;
   JV_CUDA(cudaEventCreate(&e0));

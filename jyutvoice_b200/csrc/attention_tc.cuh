@@ -2,7 +2,8 @@
 // 8 heads x 64, non-causal, keys masked by the row length (decoder.py:955-959: -1e10 bias on padded keys).
 // One CTA = 128 queries of one (row, head); keys are consumed in tiles of 64 with an online softmax:
 //   S = Q K^T      tcgen05.mma M=128 N=64  K=64      (Q, K tiles by TMA, 128B swizzle, K-major)
-//   P = softmax    one thread per query row: tcgen05.ld S, exp2, running max / sum, P -> smem (bf16, K-major)
+//   P = softmax    one thread per query row: the 64 scores of a key tile in registers (one tcgen05.ld round trip), exp2,
+//                  running max / sum with lazy rescaling, P -> smem (bf16, K-major)
 //   O += P V       tcgen05.mma M=128 N=64  K=64      (V tile by TMA is the MN-major B operand as it lies in memory)
 // O stays in TMEM across key tiles and is rescaled in place (tcgen05.ld / st) when the running max moves.
 // Four CTAs fit per SM (48 KB smem, 128 TMEM columns each): while one CTA's softmax threads work, the others' MMAs,
@@ -35,6 +36,35 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(THREADS, 4)
@@ -133,27 +163,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
+    // A warp whose 32 query rows all lie beyond the utterance (last query tile) does no math: its P rows only feed O rows
+    // that are never stored.  It still follows the barrier protocol tile by tile.
+    const bool live = q0 + q * 32 < len;
     for (int j = 0; j < nt; ++j) {
       const uint32_t ph = j & 1;
       const int k0 = j * TK;
       const int kvalid = len - k0 < TK ? len - k0 : TK;
       mbar_wait(bar_s, ph, 16);
       tc_fence_after();
-      float mx = -INFINITY;
-      const bool full = kvalid == TK;  // warp-uniform: full key tiles skip all masking arithmetic
-#pragma unroll 1
-      for (int c = 0; c < TK / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld32(tS + lane_addr + c * 32, acc);
-        if (full) {
+      if (!live) {
+        if (j > 0) mbar_wait(bar_o, ph ^ 1, 17);  // stay in step: bar_p's previous phase has completed once PV_{j-1} has
+        mbar_arrive(bar_p);
+        continue;
+      }
+      // the whole 64-key row of S in registers: one TMEM round trip per key tile
+      uint32_t s0[32], s1[32];
+      tmem_ld32_issue(tS + lane_addr, s0);
+      tmem_ld32_issue(tS + lane_addr + 32, s1);
+      tmem_ld_wait();
+      if (kvalid < TK) {  // warp-uniform: only the last key tile masks
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(acc[i]));
-        } else {
-          const int vc = kvalid - c * 32;  // valid keys in this chunk (may be <= 0)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < vc ? __uint_as_float(acc[i]) : -INFINITY);
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kvalid) s0[i] = 0xff800000u;  // -inf
+          if (i + 32 >= kvalid) s1[i] = 0xff800000u;
         }
       }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s0[i]));
+        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s1[i]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // lazy rescaling: keep the reference max unless the row max grew by more than 2^8 (p <= 256 then: harmless)
       const float m_tile = mx * scale_log2e;
       float m_new = m_run, alpha = 1.f;
@@ -170,44 +212,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
       if (j > 0 && any_rescale) {
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + lane_addr + c * 32, o);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[16];
+          tmem_ld16(tO + lane_addr + c * 16, o);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tO + lane_addr + c * 32, o);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tO + lane_addr + c * 16, o);
         }
       }
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < TK / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld32(tS + lane_addr + c * 32, acc);
-        float pv[32];
-        if (full) {
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pv[i] = fast_exp2(fmaf(__uint_as_float(acc[i]), scale_log2e, -m_new));
-            lsum += pv[i];
-          }
-        } else {
-          const int vc = kvalid - c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float t = fmaf(__uint_as_float(acc[i]), scale_log2e, -m_new);
-            pv[i] = fast_exp2(i < vc ? t : -INFINITY);  // ex2(-inf) = 0: no branch around the MUFU
-            lsum += pv[i];
-          }
-        }
-        // P[row][key]: K-major SWIZZLE_128B, 16-byte chunk = key / 8
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int chunk = c * 4 + g8;
-          sts128u(sP + swz128(row, chunk), pack_bf16(pv[8 * g8], pv[8 * g8 + 1]), pack_bf16(pv[8 * g8 + 2], pv[8 * g8 + 3]),
-                  pack_bf16(pv[8 * g8 + 4], pv[8 * g8 + 5]), pack_bf16(pv[8 * g8 + 6], pv[8 * g8 + 7]));
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(s0[i]), scale_log2e, -m_new));  // ex2(-inf) = 0 for masked keys
+        const float p1 = fast_exp2(fmaf(__uint_as_float(s1[i]), scale_log2e, -m_new));
+        ls4[i & 3] += p0;
+        ls4[i & 3] += p1;
+        s0[i] = __float_as_uint(p0);
+        s1[i] = __float_as_uint(p1);
       }
-      l_run = l_run * alpha + lsum;
+      // P[row][key]: K-major SWIZZLE_128B, 16-byte chunk = key / 8
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        sts128u(sP + swz128(row, g8), pack_bf16(__uint_as_float(s0[8 * g8]), __uint_as_float(s0[8 * g8 + 1])),
+                pack_bf16(__uint_as_float(s0[8 * g8 + 2]), __uint_as_float(s0[8 * g8 + 3])),
+                pack_bf16(__uint_as_float(s0[8 * g8 + 4]), __uint_as_float(s0[8 * g8 + 5])),
+                pack_bf16(__uint_as_float(s0[8 * g8 + 6]), __uint_as_float(s0[8 * g8 + 7])));
+        sts128u(sP + swz128(row, 4 + g8), pack_bf16(__uint_as_float(s1[8 * g8]), __uint_as_float(s1[8 * g8 + 1])),
+                pack_bf16(__uint_as_float(s1[8 * g8 + 2]), __uint_as_float(s1[8 * g8 + 3])),
+                pack_bf16(__uint_as_float(s1[8 * g8 + 4]), __uint_as_float(s1[8 * g8 + 5])),
+                pack_bf16(__uint_as_float(s1[8 * g8 + 6]), __uint_as_float(s1[8 * g8 + 7])));
+      }
+      l_run = l_run * alpha + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
       m_run = m_new;
       fence_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
       tc_fence_before();

@@ -221,6 +221,8 @@ struct GemmDesc {
   int ldo3;
   int o_stride, o_off;   // out_row = m * o_stride + o_off
   long o_rows;           // out_row must be < o_rows
+  int x_bf16;            // tcgen05 engine only: `resid` and `out_f32` point to 16-bit tensors (16-bit residual stream) ...
+  int x_in_half, x_out_half;  // ... holding fp16 (11-bit significand, stores saturate) instead of bf16
   double algo_flops;     // algorithmic FLOPs of this launch (valid frames, true N and K); profiling only
 };
 

@@ -93,8 +93,12 @@ struct Engine {
   void gemm(const GemmDesc& g, cudaStream_t st) {
     if (is_bf16()) {
       if (gemm_tc_supported(g)) launch_gemm_tc(g, tmaps, num_sms, st);
-      else gemm_lowered<bf16>(g, st);
+      else {
+        JV_REQUIRE(!g.x_bf16, JV_ERR_INVALID, "a bf16-stream GEMM must fit the tcgen05 engine");
+        gemm_lowered<bf16>(g, st);
+      }
     } else {
+      JV_REQUIRE(!g.x_bf16, JV_ERR_INVALID, "bf16 stream in fp32 mode");
       gemm_lowered<float>(g, st);
     }
   }

@@ -286,15 +286,19 @@ static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void*
   g.add_row_stride = N_RESNET * C;
   g.out_act = c.b.H; g.ldo2 = C;
   e.gemm(g, c.st);
-  // res_conv(x*m) -> RES
+  // res_conv(x*m) -> RES (bf16 mode: the residual stream X / RES is bf16)
+  const bool xb = e.is_bf16();
   g = conv_desc(c, w.res, in0, in1, 1);
-  g.out_f32 = c.b.RES; g.ldo = C;
+  if (xb) { g.out_act = c.b.RES; g.ldo2 = C; }
+  else { g.out_f32 = c.b.RES; g.ldo = C; }
   e.gemm(g, c.st);
   // x = Mish(LN(conv2(h))) * m + RES -> X ; LNX = norm1(x)
   g = conv_desc(c, w.c2, c.b.H, nullptr, 3);
   set_ln1(g, w.ln2, ACT_MISH);
   g.resid = c.b.RES; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
+  g.x_bf16 = xb;        // RES comes from a bf16-output GEMM; X is the fp16 stream
+  g.x_out_half = xb;
   set_ln2(c, g, next_ln);
   e.gemm(g, c.st);
 }
@@ -307,9 +311,11 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g.out_act = c.b.QKV; g.ldo2 = 1536;
   e.gemm(g, c.st);
   run_attention(c);
+  const bool xb = e.is_bf16();
   g = conv_desc(c, w.out, c.b.ATT, nullptr, 1);  // x += to_out(attn) ; LNX = norm3(x)
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
+  g.x_bf16 = g.x_in_half = g.x_out_half = xb;
   set_ln2(c, g, w.n3);
   e.gemm(g, c.st);
   g = conv_desc(c, w.ff1, c.b.LNX, nullptr, 1);
@@ -319,8 +325,12 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g = conv_desc(c, w.ff2, c.b.FF, nullptr, 1);  // x += ff(norm3(x)) ; LNX = next norm1(x)
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
+  g.x_bf16 = g.x_in_half = g.x_out_half = xb;
   if (next_ln) set_ln2(c, g, *next_ln);
-  if (copy_to) { g.out_act = copy_to; g.ldo2 = C; }
+  if (copy_to) {
+    if (xb) { g.out_f32 = (float*)copy_to; g.x_out_half = 0; }  // bf16 copy for the next conv; X is not read again in this group
+    else { g.out_act = copy_to; g.ldo2 = C; }
+  }
   e.gemm(g, c.st);
 }
 

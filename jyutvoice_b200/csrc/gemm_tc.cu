@@ -59,7 +59,7 @@ struct KernelEntry {
   int epi;
   KernelFn fn;
 };
-constexpr int N_KERNELS = 9;
+constexpr int N_KERNELS = 12;
 // the epilogue shapes the estimator / HiFT graphs actually use, plus the run-time generic kernel (last)
 static const KernelEntry* kernel_table() {
   using namespace tc;
@@ -72,6 +72,10 @@ static const KernelEntry* kernel_table() {
       {EPI_F32, gemm_taps_tc_kernel<EPI_F32>},                                                // res_conv, final_proj, conv_post
       {EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_RESID | EPI_F32>},                        // HiFT ups + source, last conv2
       {EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_F32 | EPI_OACT>},                          // HiFT source_downs (im2col)
+      // bf16 residual stream (estimator, bf16 mode)
+      {EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2>},
+      {EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>},
+      {EPI_XB | EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32>},
       {-1, gemm_taps_tc_kernel<-1>},
   };
   return t;
@@ -135,8 +139,9 @@ bool gemm_tc_supported(const GemmDesc& g) {
     if (!aligned16(g.A[s]) || g.lda[s] % 8 != 0 || g.lda[s] < g.K_tap) return false;
   }
   if (!aligned16(g.W)) return false;
-  if (g.resid && (!aligned16(g.resid) || g.ldr % 4 != 0)) return false;
-  if (g.out_f32 && (!aligned16(g.out_f32) || g.ldo % 4 != 0)) return false;
+  if (g.resid && (!aligned16(g.resid) || g.ldr % (g.x_bf16 ? 8 : 4) != 0)) return false;
+  if (g.out_f32 && (!aligned16(g.out_f32) || g.ldo % (g.x_bf16 ? 8 : 4) != 0)) return false;
+  if (g.x_bf16 && (!g.resid || !g.out_f32 || g.out_act)) return false;  // bf16 stream: residual in, stream out (+ LayerNorm out)
   if (g.out_act && (!aligned16(g.out_act) || g.ldo2 % 8 != 0)) return false;
   if (g.out_ln && (!aligned16(g.out_ln) || g.ldo3 % 8 != 0)) return false;
   if ((g.ln1_gamma || g.ln2_gamma || g.add_row) && g.N != 256) return false;
@@ -168,7 +173,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   const long Ktot = (long)g.n_taps * g.K_tap;
   const int k_iters = (int)(Ktot / tc::BLOCK_K);
   const int epi = (g.ln1_gamma ? tc::EPI_LN1 : 0) | (g.resid ? tc::EPI_RESID : 0) | (g.out_f32 ? tc::EPI_F32 : 0) |
-                  (g.out_act ? tc::EPI_OACT : 0) | (g.ln2_gamma ? tc::EPI_LN2 : 0);
+                  (g.out_act ? tc::EPI_OACT : 0) | (g.ln2_gamma ? tc::EPI_LN2 : 0) | (g.x_bf16 ? tc::EPI_XB : 0);
   // Slab mode (stride-1 conv, one source, resident weights): see TcParams.
   int min_shift = 0, max_shift = 0;
   bool one_src = true;
@@ -199,6 +204,11 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
     const bool f_resid = epi & tc::EPI_RESID, f_f32 = epi & tc::EPI_F32, f_oact = epi & tc::EPI_OACT;
     int off = 0;
     p.off_R = 0;
+    if (g.x_bf16) {  // R0 R1 | O0 | O1, 2 KB each
+      p.off_OF = 2 * tc::EPI_B16_BYTES;
+      p.off_OB = 3 * tc::EPI_B16_BYTES;
+      off = 4 * tc::EPI_B16_BYTES;
+    } else {
     if (f_resid) off += tc::EPI_F32_BYTES;
     p.off_OF = off;
     if (f_f32) {
@@ -210,6 +220,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
       off += tc::EPI_B16_BYTES;
       if (wide && p.wres) p.off_OB = p.off_OF;
       else { p.off_OB = off; off += tc::EPI_B16_BYTES; }
+    }
     }
     p.epi_bytes_per_warp = round_up(off, 1024);
   }
@@ -274,8 +285,8 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   p.cluster = (!p.wres && m_tiles >= 2 && p.block_n % 16 == 0 && use_cluster()) ? 2 : 1;
   p.num_units = p.wres ? m_tiles : cdiv(m_tiles, p.cluster) * p.n_tiles_n;
   tm.w = cache.get(g.W, Ktot, g.N, Ktot * 2, tc::BLOCK_K, p.block_n / p.cluster, 0);
-  tm.resid = g.resid ? out_view(cache, g, g.resid, g.ldr, 4, 1) : tm.a0;
-  tm.out_f32 = g.out_f32 ? out_view(cache, g, g.out_f32, g.ldo, 4, 1) : tm.a0;
+  tm.resid = g.resid ? out_view(cache, g, g.resid, g.ldr, g.x_bf16 ? 2 : 4, g.x_bf16 ? 2 : 1) : tm.a0;
+  tm.out_f32 = g.out_f32 ? out_view(cache, g, g.out_f32, g.ldo, g.x_bf16 ? 2 : 4, g.x_bf16 ? 2 : 1) : tm.a0;
   tm.out_act = g.out_act ? out_view(cache, g, g.out_act, g.ldo2, 2, 2) : tm.a0;
   tm.out_ln = g.out_ln ? out_view(cache, g, g.out_ln, g.ldo3, 2, 2) : tm.a0;
   int grid = p.num_units * p.cluster < num_sms ? p.num_units * p.cluster : num_sms;
@@ -304,8 +315,10 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 2 : 1;
   KernelFn fn = kernel_table()[N_KERNELS - 1].fn;  // generic
+  bool found = false;
   for (int i = 0; i < N_KERNELS - 1; ++i)
-    if (kernel_table()[i].epi == epi) fn = kernel_table()[i].fn;
+    if (kernel_table()[i].epi == epi) { fn = kernel_table()[i].fn; found = true; }
+  JV_REQUIRE(found || !g.x_bf16, JV_ERR_INVALID, "no bf16-stream kernel for epilogue kind %d", epi);
   JV_CUDA(cudaLaunchKernelEx(&cfg, fn, tm, g, p));
   JV_LAUNCHED();
   if (ps.on) {

@@ -16,6 +16,7 @@
 // zero-fills rows outside the tensor, and the packed activation layout keeps >= |shift| zero rows
 // between utterances, which is exactly the conv's zero padding.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace jv {
@@ -305,6 +306,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// two floats -> packed fp16, round to nearest, saturating at +-65504 (no inf can enter the residual stream)
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -327,6 +334,10 @@ __device__ __forceinline__ void stage_store_b16(const CUtensorMap* tm, uint32_t 
 // EPI: compile-time epilogue feature mask (specialised instantiations keep the per-chunk instruction stream short);
 // EPI < 0 is the generic kernel that tests the descriptor at run time.
 constexpr int EPI_LN1 = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_OACT = 8, EPI_LN2 = 16;
+// EPI_XB: the residual stream is bf16 (GemmDesc::x_bf16): `resid` in and the main output are 2 KB bf16 chunks, so the
+// same 8 KB of staging per warp holds two residual chunks in flight and two output buffers (no store is ever waited for
+// right after it was issued).  The fp32-stream kernels move twice the bytes with half the loads in flight.
+constexpr int EPI_XB = 32;
 
 template <int EPI>
 __global__ void __launch_bounds__(EPI == EPI_OACT ? NUM_THREADS_WIDE : NUM_THREADS, 1)
@@ -336,6 +347,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const bool F_F32 = EPI >= 0 ? (EPI & EPI_F32) != 0 : g.out_f32 != nullptr;
   const bool F_OACT = EPI >= 0 ? (EPI & EPI_OACT) != 0 : g.out_act != nullptr;
   const bool F_LN2 = EPI >= 0 ? (EPI & EPI_LN2) != 0 : g.ln2_gamma != nullptr;
+  constexpr bool XB = EPI >= 0 && (EPI & EPI_XB) != 0;
   constexpr int N_EPI_WARPS = EPI == EPI_OACT ? EPI_WARPS_MAX : EPI_WARPS;
   constexpr int N_SUB = N_EPI_WARPS / 4;  // warps sharing one TMEM lane quarter: they split the 32-column chunks of a tile
   extern __shared__ uint8_t smem_raw[];
@@ -586,7 +598,16 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const float* v_b2 = p.vec_ln2 ? smf + p.vec_ln2 / 4 + p.block_n - n0 : g.ln2_beta;
       const float* v_act = g.act_vec ? (p.vec_act ? smf + p.vec_act / 4 - n0 : g.act_vec) : nullptr;
       const float* v_act2 = g.act2_vec ? (p.vec_act2 ? smf + p.vec_act2 / 4 - n0 : g.act2_vec) : nullptr;
-      if (F_RESID && lane == 0) {  // residual of the first chunk: in flight while the accumulator is still being computed
+      if (XB) {  // residual of the first two chunks: in flight while the accumulator is still being computed
+        if (lane == 0) {
+          mbar_expect_tx(ebar, EPI_B16_BYTES);
+          tma_load_2d(&tm.resid, ebar, sR, n0 + c_first * 32, row0);
+          if ((c_first + c_step) * 32 < g.N - n0) {
+            mbar_expect_tx(ebar + 8, EPI_B16_BYTES);
+            tma_load_2d(&tm.resid, ebar + 8, sR + EPI_B16_BYTES, n0 + (c_first + c_step) * 32, row0);
+          }
+        }
+      } else if (F_RESID && lane == 0 && !(p.debug & 512)) {  // residual of the first chunk: in flight while the accumulator is still being computed
         if (F_LN2) bulk_wait_read0();  // the previous tile's post-LayerNorm stores may still be reading R
         mbar_expect_tx(ebar, EPI_F32_BYTES);
         tma_load_2d(&tm.resid, ebar, sR, n0 + c_first * 32, row0);
@@ -625,7 +646,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       // ---- main pass
       float sum2 = 0.f, sq2 = 0.f;
       const int n_chunks_valid = (g.N - n0 + 31) / 32 < n_chunks ? (g.N - n0 + 31) / 32 : n_chunks;
-      for (int c = c_first; c < ((p.debug & 2) ? 0 : n_chunks_valid); c += c_step) {
+      int i_chunk = 0;
+      for (int c = c_first; c < ((p.debug & 2) ? 0 : n_chunks_valid); c += c_step, ++i_chunk) {
         const int n = n0 + c * 32;
         const int n_valid = g.N - n < 32 ? g.N - n : 32;
         uint32_t acc[32];
@@ -644,7 +666,35 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-        if (F_RESID) {
+        if (XB) {
+          const int ib = i_chunk & 1;
+          mbar_wait(ebar + 8 * ib, (ephase >> ib) & 1, 5);
+          ephase ^= 1u << ib;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 r = lds128(sR + ib * EPI_B16_BYTES + swz64(lane, j));
+            const uint32_t w[4] = {__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z), __float_as_uint(r.w)};
+            if (g.x_in_half) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+                v[8 * j + 2 * k] += f.x;
+                v[8 * j + 2 * k + 1] += f.y;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // bf16 -> fp32 is a 16-bit shift
+                v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+                v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+              }
+            }
+          }
+          __syncwarp();  // every lane has read this R buffer: refill it with the residual two chunks ahead
+          if (lane == 0 && c + 2 * c_step < n_chunks_valid) {
+            mbar_expect_tx(ebar + 8 * ib, EPI_B16_BYTES);
+            tma_load_2d(&tm.resid, ebar + 8 * ib, sR + ib * EPI_B16_BYTES, n + 64 * c_step, row0);
+          }
+        } else if (F_RESID && !(p.debug & 512)) {
           mbar_wait(ebar, ephase, 5);
           ephase ^= 1;
 #pragma unroll
@@ -668,14 +718,26 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           tmem_st32(taddr + c * 32, acc);
         }
         // output staging: wait (late) for the stores that last used the buffers
-        const uint32_t hbuf = F_F32 ? sOB : ((n_out & 1) ? sOB : sOF);
+        const uint32_t hbuf = (F_F32 && !XB) ? sOB : ((n_out & 1) ? sOB : sOF);
         ++n_out;
         if (lane == 0) {
-          if (F_F32 || one_buf) bulk_wait_read0();
+          if ((F_F32 && !XB) || one_buf) bulk_wait_read0();
           else bulk_wait_read1();
         }
         __syncwarp();
-        if (F_F32) {
+        if (XB) {  // the stream value itself, rounded to fp16 (stream) or bf16 (the copy that feeds the next conv)
+          if (g.x_out_half) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128u(hbuf + swz64(lane, j), pack_f16_sat(v[8 * j], v[8 * j + 1]), pack_f16_sat(v[8 * j + 2], v[8 * j + 3]),
+                      pack_f16_sat(v[8 * j + 4], v[8 * j + 5]), pack_f16_sat(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128u(hbuf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                      pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
+        } else if (F_F32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) sts128(sOF + swz128(lane, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
@@ -689,7 +751,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         if (!(p.debug & 16)) fence_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.debug & 1)) {
-          if (F_F32) tma_store_2d(&tm.out_f32, sOF, n, row0);
+          if (XB) tma_store_2d(&tm.out_f32, hbuf, n, row0);
+          else if (F_F32) tma_store_2d(&tm.out_f32, sOF, n, row0);
           if (F_OACT) tma_store_2d(&tm.out_act, hbuf, n, row0);
           bulk_commit();
         }
@@ -713,11 +776,16 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           if (lane == 0) {  // alternate OF / OB as bf16 buffers; the first two chunks wait for the main pass's stores
-            if (n_ln < 2) bulk_wait_read0();
+            if (n_ln < 2 && !XB) bulk_wait_read0();
             else bulk_wait_read1();
           }
           __syncwarp();
-          stage_store_b16(&tm.out_ln, (n_ln & 1) ? sOB : sOF, lane, v, n, row0);
+          if (XB) {  // the main pass's alternation simply continues
+            stage_store_b16(&tm.out_ln, (n_out & 1) ? sOB : sOF, lane, v, n, row0);
+            ++n_out;
+          } else {
+            stage_store_b16(&tm.out_ln, (n_ln & 1) ? sOB : sOF, lane, v, n, row0);
+          }
         }
       }
       tc_fence_before();

@@ -18,6 +18,9 @@ cases = [
     ("FF1      N=1024 K=256  GELU bf16", M, 1024, 256, 1, 16 | 2),
     ("out-proj N=256  K=512  resid f32 + LN2", M, 256, 512, 1, 1 | 8),
     ("out-proj N=256  K=512  resid f32", M, 256, 512, 1, 1),
+    ("xb16 out-proj N=256 K=512 resid + LN2", M, 256, 512, 1, 1 | 8 | 32),
+    ("xb16 FF2 N=256 K=1024 resid + LN2", M, 256, 1024, 1, 1 | 8 | 32),
+    ("xb16 conv N=256 K=3x256 LN1+Mish+resid+LN2", M, 256, 256, 3, 1 | 4 | 8 | 32),
     ("FF2      N=256  K=1024 resid f32 + LN2", M, 256, 1024, 1, 1 | 8),
     ("conv     N=256  K=3x256 plain bf16", M, 256, 256, 3, 16),
     ("conv     N=256  K=3x256 LN1+Mish bf16", M, 256, 256, 3, 16 | 4),
