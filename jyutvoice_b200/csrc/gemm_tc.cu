@@ -44,14 +44,16 @@ ProfileState& profile_state() {
   return s;
 }
 
-// JYUTVOICE_B200_CLUSTER=0 disables the 2-CTA weight multicast (debugging aid)
-static bool use_cluster() {
+// JYUTVOICE_B200_CLUSTER=n: CTAs per cluster for the weight multicast (0 / 1 disables it; debugging aid)
+static int cluster_size() {  // CTAs per cluster for the weight multicast: 0 / 1 = off (default)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("JYUTVOICE_B200_CLUSTER");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = e ? atoi(e) : 1;  // measured on B200: 1 >= 2 >> 4 for every estimator shape (profiles/r1j_cluster_sweep.txt)
+    if (v < 1) v = 1;
+    if (v > 8) v = 8;
   }
-  return v == 1;
+  return v;
 }
 
 typedef void (*KernelFn)(const tc::TcMaps, const GemmDesc, const tc::TcParams);
@@ -282,7 +284,9 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   tc::TcMaps tm;
   tm.a0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], (long)g.lda[0] * 2, tc::BLOCK_K, p.slab ? p.slab_rows : tc::BLOCK_M, 0);
   tm.a1 = g.A[1] ? cache.get(g.A[1], g.K_tap, g.a_rows[1], (long)g.lda[1] * 2, tc::BLOCK_K, tc::BLOCK_M, 0) : tm.a0;
-  p.cluster = (!p.wres && m_tiles >= 2 && p.block_n % 16 == 0 && use_cluster()) ? 2 : 1;
+  p.cluster = 1;
+  for (int cs = cluster_size(); cs >= 2; cs >>= 1)
+    if (!p.wres && m_tiles >= cs && p.block_n % (8 * cs) == 0 && num_sms % cs == 0) { p.cluster = cs; break; }
   p.num_units = p.wres ? m_tiles : cdiv(m_tiles, p.cluster) * p.n_tiles_n;
   tm.w = cache.get(g.W, Ktot, g.N, Ktot * 2, tc::BLOCK_K, p.block_n / p.cluster, 0);
   tm.resid = g.resid ? out_view(cache, g, g.resid, g.ldr, g.x_bf16 ? 2 : 4, g.x_bf16 ? 2 : 1) : tm.a0;
