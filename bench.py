@@ -26,6 +26,21 @@ UNIT = "audio-s/s"
 FRAMES_PER_SEC = 50.0  # 24000 / 480
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` summary (profiles/*_gemm_traffic.json); None if there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+        return float(d["avg_dram_bytes_per_launch"]), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -237,9 +252,11 @@ def run_ours(args):
         peaks = load_peaks()
         achieved = kfl.value / (kms.value * 1e-3) / 1e12 if kms.value > 0 else 0.0
         nprof = max(1, min(args.steps, 2))
+        traffic, traffic_src = load_traffic()
         roof = {"bound": "tensor", "kernel": "gemm_taps_tc_kernel (tcgen05 bf16, all conv / linear contractions)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["src"] + " sustained bf16",
+                "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
+                "traffic_source": traffic_src, "peak_source": peaks["src"] + " sustained bf16",
                 "launches_per_step": kn.value / nprof, "kernel_ms_per_step": kms.value / nprof,
                 "algo_tflop_per_step": kfl.value / nprof / 1e12, "share_of_step": (kms.value / nprof) / (ms / args.steps)}
 

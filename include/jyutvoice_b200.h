@@ -60,6 +60,11 @@ int jv_estimator_set_weight(jv_estimator* h, const char* key, const float* data,
 /* Fails (JV_ERR_STATE, listing the first missing key) unless all 910 tensors were set. */
 int jv_estimator_finalize(jv_estimator* h);
 
+/* streaming=True of CausalConditionalDecoder.forward (flow/decoder.py:950-953, utils/mask.py:91-126): attention query t
+ * sees keys < min(len, (t / chunk_size + 1) * chunk_size).  chunk_size = static_chunk_size (50) turns it on, 0 (the
+ * default) restores full context.  State of the handle: applies to every later jv_estimator_forward / jv_cfm_solve. */
+int jv_estimator_set_chunk(jv_estimator* h, int chunk_size);
+
 /* Workspace for B utterances (R = 2B estimator rows with CFG) of the given lengths. */
 size_t jv_cfm_workspace_bytes(const jv_estimator* h, int n_rows, const int32_t* lens_host);
 

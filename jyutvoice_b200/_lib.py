@@ -32,6 +32,7 @@ SIGNATURES = {
     "jv_estimator_destroy": (None, [c_void_p]),
     "jv_estimator_set_weight": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, P_i64, c_int]),
     "jv_estimator_finalize": (c_int, [c_void_p]),
+    "jv_estimator_set_chunk": (c_int, [c_void_p, c_int]),
     "jv_cfm_workspace_bytes": (c_size_t, [c_void_p, c_int, P_i32]),
     "jv_cfm_solve_workspace_bytes": (c_size_t, [c_void_p, c_int, P_i32]),
     "jv_estimator_forward": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, P_f32, c_void_p, c_void_p,

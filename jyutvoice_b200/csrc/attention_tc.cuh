@@ -69,13 +69,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 
 __global__ void __launch_bounds__(THREADS, 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmKV, bf16* __restrict__ out, int ldo, const int* __restrict__ row_off,
-                    const int* __restrict__ row_len, float scale_log2e) {
+                    const int* __restrict__ row_len, float scale_log2e, int chunk) {
   using namespace tc;
   const int r = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
   const int len = row_len[r];
   if (q0 >= len) return;
   const int off = row_off[r];
-  const int nt = (len + TK - 1) / TK;
+  // streaming=True (decoder.py:950-953): query t sees keys < min(len, (t / chunk + 1) * chunk); chunk = 0: all keys
+  const int kend = chunk > 0 ? min(len, ((q0 + TQ - 1) / chunk + 1) * chunk) : len;
+  const int nt = (kend + TK - 1) / TK;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -166,10 +168,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     // A warp whose 32 query rows all lie beyond the utterance (last query tile) does no math: its P rows only feed O rows
     // that are never stored.  It still follows the barrier protocol tile by tile.
     const bool live = q0 + q * 32 < len;
+    const int klim = chunk > 0 ? min(len, ((q0 + row) / chunk + 1) * chunk) : len;  // per query row in streaming mode
     for (int j = 0; j < nt; ++j) {
       const uint32_t ph = j & 1;
       const int k0 = j * TK;
-      const int kvalid = len - k0 < TK ? len - k0 : TK;
+      const int kvalid = klim - k0;  // visible keys of this tile for this row (<= 0: none, >= TK: all)
       mbar_wait(bar_s, ph, 16);
       tc_fence_after();
       if (!live) {
@@ -182,7 +185,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       tmem_ld32_issue(tS + lane_addr, s0);
       tmem_ld32_issue(tS + lane_addr + 32, s1);
       tmem_ld_wait();
-      if (kvalid < TK) {  // warp-uniform: only the last key tile masks
+      if (kvalid < TK) {  // full context: warp-uniform, only the last key tile masks
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i >= kvalid) s0[i] = 0xff800000u;  // -inf
@@ -281,7 +284,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 }  // namespace attn
 
 static inline void launch_attention_tc(TmapCache& cache, const void* qkv, void* out, const int* row_off, const int* row_len,
-                                       long M_alloc, int R, int Tmax_len, cudaStream_t st) {
+                                       long M_alloc, int R, int Tmax_len, int chunk, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     JV_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
@@ -302,7 +305,7 @@ static inline void launch_attention_tc(TmapCache& cache, const void* qkv, void* 
   cfg.attrs = lattr;
   cfg.numAttrs = 1;
   JV_CUDA(cudaLaunchKernelEx(&cfg, attn::attention_tc_kernel, tm, tmkv, (bf16*)out, 512, row_off, row_len,
-                             0.125f * 1.4426950408889634f));
+                             0.125f * 1.4426950408889634f, chunk));
   JV_LAUNCHED();
 }
 

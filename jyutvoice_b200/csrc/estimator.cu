@@ -42,6 +42,7 @@ struct jv_estimator {
   WeightStore store;
   DeviceAlloc mem;
   bool finalized = false;
+  int chunk = 0;  // attention chunk mask of streaming=True (decoder.py:950-953); 0 = full context
   GroupW groups[N_RESNET];  // 0 = down, 1..12 = mid, 13 = up
   PackedW down_conv, up_conv, final_conv, final_proj;
   LNW final_ln;
@@ -248,7 +249,7 @@ static GemmDesc conv_desc(const FwdCtx& c, const PackedW& w, const void* A0p, co
 
 static void run_attention(const FwdCtx& c) {
   if (c.h->eng.is_bf16()) {  // tcgen05 flash-style kernel
-    launch_attention_tc(c.h->eng.tmaps, c.b.QKV, c.b.ATT, c.b.row_off, c.b.row_len, c.M_alloc, c.R, c.Tmax_len, c.st);
+    launch_attention_tc(c.h->eng.tmaps, c.b.QKV, c.b.ATT, c.b.row_off, c.b.row_len, c.M_alloc, c.R, c.Tmax_len, c.h->chunk, c.st);
     return;
   }
   static bool attr = false;
@@ -258,7 +259,7 @@ static void run_attention(const FwdCtx& c) {
   }
   dim3 grid(cdiv(c.Tmax_len, 64), 8, c.R);
   attention_simt_kernel<float><<<grid, 256, ATT_SMEM_BYTES, c.st>>>((const float*)c.b.QKV, 1536, (float*)c.b.ATT, 512, c.b.row_off,
-                                                                    c.b.row_len, 0.125f);
+                                                                    c.b.row_len, 0.125f, c.h->chunk);
   JV_LAUNCHED();
 }
 
@@ -445,6 +446,13 @@ int jv_estimator_create(int device, int precision, jv_estimator** out) {
 }
 
 void jv_estimator_destroy(jv_estimator* h) { delete h; }
+
+int jv_estimator_set_chunk(jv_estimator* h, int chunk_size) {
+  JV_API_BEGIN
+  JV_REQUIRE(h && chunk_size >= 0, JV_ERR_INVALID, "bad arguments");
+  h->chunk = chunk_size;
+  JV_API_END
+}
 
 int jv_estimator_set_weight(jv_estimator* h, const char* key, const float* data, const int64_t* shape, int ndim) {
   JV_API_BEGIN

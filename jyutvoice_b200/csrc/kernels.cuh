@@ -152,7 +152,7 @@ constexpr int ATT_SMEM_BYTES = 4 * 64 * ATT_PAD * (int)sizeof(float);
 template <typename TA>
 __global__ void __launch_bounds__(256) attention_simt_kernel(const TA* __restrict__ qkv, int ld, TA* __restrict__ out, int ldo,
                                                              const int* __restrict__ row_off, const int* __restrict__ row_len,
-                                                             float scale) {
+                                                             float scale, int chunk) {
   extern __shared__ float att_smem[];
   float (*Qt)[ATT_PAD] = reinterpret_cast<float (*)[ATT_PAD]>(att_smem);                      // [d][q]
   float (*Kt)[ATT_PAD] = reinterpret_cast<float (*)[ATT_PAD]>(att_smem + 64 * ATT_PAD);       // [d][k]
@@ -184,7 +184,15 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const TA* __restric
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   }
 
-  for (int k0 = 0; k0 < len; k0 += 64) {
+  // streaming=True (decoder.py:950-953): query t sees keys < min(len, (t / chunk + 1) * chunk); chunk = 0: all keys
+  int klim[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = q0 + ty * 4 + i;
+    klim[i] = chunk > 0 ? min(len, (t / chunk + 1) * chunk) : len;
+  }
+  const int kend = chunk > 0 ? min(len, ((q0 + 63) / chunk + 1) * chunk) : len;
+  for (int k0 = 0; k0 < kend; k0 += 64) {
     __syncthreads();  // previous iteration done with Kt/Vs/Ps (and Q stores visible on first pass)
     for (int i = warp; i < 64; i += 8) {
       const int t = k0 + i;
@@ -224,12 +232,12 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const TA* __restric
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int kidx = k0 + tx * 4 + j;
-        s[i][j] = kidx < len ? s[i][j] * scale : -INFINITY;
+        s[i][j] = kidx < klim[i] ? s[i][j] * scale : -INFINITY;
         mx = fmaxf(mx, s[i][j]);
       }
 #pragma unroll
       for (int w = 8; w > 0; w >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, w));
-      const float mnew = fmaxf(mrow[i], mx);  // finite: every tile holds >= 1 valid key
+      const float mnew = fmaxf(mrow[i], mx);  // finite: the first tile holds >= 1 visible key for every row
       const float corr = expf(mrow[i] - mnew);
       float ps = 0.f;
 #pragma unroll

@@ -5,7 +5,7 @@
 
 Differences, all supersets: any batch size (the reference is batch-1: flow_matching.py:238-243), ragged
 lengths given by the prefix `mask`, and a `precision` kwarg ("bf16" tcgen05 tensor cores / "fp32" FFMA).
-`streaming=True` (chunk masks) is not part of this path and raises.
+`streaming=True` applies the reference's static chunk mask (chunk = static_chunk_size) inside the attention kernels.
 """
 import ctypes
 import os
@@ -104,8 +104,6 @@ class CausalConditionalDecoder(nn.Module):
     @torch.inference_mode()
     def forward(self, x, mask, mu, t, spks=None, cond=None, streaming=False):
         """Reference signature (decoder.py:917).  x, mu, cond [R,80,T]; mask [R,1,T]; t [R]; spks [R,80]."""
-        if streaming:
-            raise NotImplementedError("streaming chunk masks are outside this path")
         dev = x.device
         h = self.handle(dev)
         R, _, T = x.shape
@@ -121,6 +119,7 @@ class CausalConditionalDecoder(nn.Module):
         p = lambda z: ctypes.c_void_p(0 if z is None else z.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
+            _lib.check(L.jv_estimator_set_chunk(h, int(self.static_chunk_size) if streaming else 0))
             _lib.check(L.jv_estimator_forward(h, R, T, lens_c, p(x_), p(mu_), t_host, p(spks_), p(cond_), p(out),
                                               p(ws), ws.numel(), stream))
         return out
@@ -155,8 +154,6 @@ class CausalConditionalCFM(nn.Module):
     def forward(self, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None, streaming=False, lengths=None):
         """Reference signature (flow_matching.py:357-401) -> (mel fp32 [B,80,T], None).
         `lengths` (host ints) may replace `mask` to skip the device->host read of the mask."""
-        if streaming:
-            raise NotImplementedError("streaming chunk masks are outside this path")
         if not isinstance(self.estimator, CausalConditionalDecoder):
             raise TypeError("estimator must be a jyutvoice_b200 CausalConditionalDecoder")
         dev = mu.device
@@ -186,6 +183,7 @@ class CausalConditionalCFM(nn.Module):
         p = lambda z: ctypes.c_void_p(0 if z is None else z.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
+            _lib.check(L.jv_estimator_set_chunk(h, int(self.estimator.static_chunk_size) if streaming else 0))
             _lib.check(L.jv_cfm_solve(h, B, T, lens_c, p(mu_), p(spks_), p(cond_), p(noise), noise.shape[1],
                                       float(temperature), int(n_timesteps), t_c, float(self.inference_cfg_rate),
                                       p(out), p(ws), ws.numel(), stream))

@@ -79,18 +79,26 @@ def tblock(sd, name, x, bias):
     return F.linear(h, sd[name + ".ff.net.2.weight"], sd[name + ".ff.net.2.bias"]) + x
 
 
-def attn_bias(mask, t_len):
-    """decoder.py:955-959 (streaming=False): key-padding mask repeated over queries -> (1-m)*-1e10."""
+def attn_bias(mask, t_len, chunk=0):
+    """decoder.py:950-959: key-padding mask repeated over queries (streaming=False), or AND-ed with the static chunk
+    mask (streaming=True: query i sees keys < (i // chunk + 1) * chunk, mask.py:91-126, 180-187) -> (1-m)*-1e10."""
     m = mask.bool()  # [R,1,T]
+    if chunk > 0:
+        i = torch.arange(t_len)
+        ending = torch.clamp((i // chunk + 1) * chunk, max=t_len)
+        cm = torch.arange(t_len)[None, :] < ending[:, None]  # [T,T]
+        m = m & cm[None]
+    else:
+        m = m.repeat(1, t_len, 1)
     if (m.sum(dim=-1) == 0).any():  # mask.py:202-206 repairs all-masked rows
         m = m.clone()
         m[m.sum(dim=-1) == 0] = True
-    m = m.repeat(1, t_len, 1)
     return (1.0 - m.to(mask.dtype)) * -1.0e10
 
 
-def estimator_forward(sd, x, mask, mu, t, spks=None, cond=None, p="estimator."):
-    """CausalConditionalDecoder.forward, streaming=False.  x,mu,cond [R,80,T]; mask [R,1,T]; t [R]."""
+def estimator_forward(sd, x, mask, mu, t, spks=None, cond=None, p="estimator.", chunk=0):
+    """CausalConditionalDecoder.forward; chunk = static_chunk_size (50) for streaming=True, 0 for streaming=False.
+    x,mu,cond [R,80,T]; mask [R,1,T]; t [R]."""
     temb = time_embedding(sd, t, p)
     h = torch.cat([x, mu], dim=1)
     if spks is not None:
@@ -98,7 +106,7 @@ def estimator_forward(sd, x, mask, mu, t, spks=None, cond=None, p="estimator."):
     if cond is not None:
         h = torch.cat([h, cond], dim=1)
     T = h.shape[-1]
-    bias = attn_bias(mask, T)
+    bias = attn_bias(mask, T, chunk)
 
     def group(h, rname, tname):
         h = resnet(sd, rname, h, mask, temb)
@@ -127,7 +135,7 @@ def t_span_cosine(n_timesteps, dtype=torch.float32):
 
 
 def cfm_forward(sd, noise_bank, mu, mask, n_timesteps, temperature=1.0, spks=None, cond=None,
-                cfg_rate=CFG_RATE, p="estimator."):
+                cfg_rate=CFG_RATE, p="estimator.", chunk=0):
     """CausalConditionalCFM.forward + solve_euler for ONE utterance (B=1, the reference's only mode)."""
     assert mu.shape[0] == 1
     T = mu.shape[2]
@@ -143,7 +151,7 @@ def cfm_forward(sd, noise_bank, mu, mask, n_timesteps, temperature=1.0, spks=Non
         t_in = torch.cat([t, t], dim=0)
         spks_in = torch.cat([spks, torch.zeros_like(spks)], dim=0)
         cond_in = torch.cat([cond, zeros], dim=0)
-        v = estimator_forward(sd, x_in, mask_in, mu_in, t_in, spks_in, cond_in, p)
+        v = estimator_forward(sd, x_in, mask_in, mu_in, t_in, spks_in, cond_in, p, chunk)
         v = (1.0 + cfg_rate) * v[0:1] - cfg_rate * v[1:2]
         x = x + dt * v
         t = t + dt

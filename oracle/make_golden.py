@@ -122,6 +122,16 @@ def main():
         mel, _ = cfm(mu, torch.ones(1, 1, 40), 5, 0.8, spks, cond)
         np.savez_compressed(os.path.join(OUT, "cfm_T40_n5_cond.npz"), seed=9, T=40, n_timesteps=5, temperature=0.8,
                             out=mel.numpy(), weight_checksum=np.array(cs))
+        # streaming=True (static chunk mask, chunk 50): decoder.py:950-953
+        lens = [120, 70, 101]
+        x, mask, mu, t, spks, cond = est_inputs(15, 3, 120, lens)
+        v = cfm.estimator(x, mask, mu, t, spks, cond, streaming=True)
+        np.savez_compressed(os.path.join(OUT, "estimator_fwd_stream.npz"), seed=15, R=3, T=120, lens=np.array(lens),
+                            out=v.numpy(), weight_checksum=np.array(cs))
+        mu, spks = cfm_inputs(17, 130)
+        mel, _ = cfm(mu, torch.ones(1, 1, 130), 3, 1.0, spks, torch.zeros(1, 80, 130), streaming=True)
+        np.savez_compressed(os.path.join(OUT, "cfm_T130_n3_stream.npz"), seed=17, T=130, n_timesteps=3, out=mel.numpy(),
+                            weight_checksum=np.array(cs))
     del cfm
 
     # ---------------- HiFT ----------------

@@ -86,6 +86,35 @@ def test_estimator_forward_golden(cfms, prec):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_streaming_golden(cfms, prec):
+    """streaming=True (static chunk mask, chunk 50) against the reference's own streaming outputs, then back to full
+    context on the same handle (the chunk is state of the handle)."""
+    from oracle.make_golden import est_inputs, cfm_inputs
+    g = np.load(os.path.join(GOLDEN, "estimator_fwd_stream.npz"))
+    x, mask, mu, t, spks, cond = est_inputs(int(g["seed"]), int(g["R"]), int(g["T"]), list(g["lens"]))
+    args = (x.cuda(), mask.cuda(), mu.cuda(), t.cuda(), spks.cuda(), cond.cuda())
+    v = cfms[prec].estimator(*args, streaming=True).cpu()
+    ref = torch.from_numpy(g["out"])
+    err = (v - ref).abs().max().item()
+    if prec == "fp32":
+        assert err <= 1e-4
+    else:
+        assert err <= BF16_MEL_TOL and rel_rms(v, ref) <= BF16_MEL_RELRMS
+    v_full = cfms[prec].estimator(*args, streaming=False).cpu()
+    assert (v_full - ref).abs().max().item() > 1e-2  # the mask is really applied, and really switched off again
+    g = np.load(os.path.join(GOLDEN, "cfm_T130_n3_stream.npz"))
+    T, n = int(g["T"]), int(g["n_timesteps"])
+    mu, spks = cfm_inputs(int(g["seed"]), T)
+    mel, _ = cfms[prec](mu.cuda(), torch.ones(1, 1, T).cuda(), n, 1.0, spks.cuda(), torch.zeros(1, 80, T).cuda(), streaming=True)
+    ref = torch.from_numpy(g["out"])
+    err = (mel.cpu() - ref).abs().max().item()
+    if prec == "fp32":
+        assert err <= FP32_MEL_TOL
+    else:
+        assert err <= BF16_MEL_TOL and rel_rms(mel.cpu(), ref) <= BF16_MEL_RELRMS
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["cfm_T33_n4", "cfm_T50_n10", "cfm_T40_n5_cond"])
 def test_cfm_golden(cfms, prec, name):
     from oracle.make_golden import cfm_inputs
@@ -155,8 +184,10 @@ def test_cfm_errors(cfms):
         cfm(mu, None, 2, spks=torch.zeros(2, 80).cuda(), lengths=[10, 11])
     with pytest.raises(ValueError):
         cfm(mu, None, 2, spks=torch.zeros(2, 80).cuda(), lengths=[10, 0])
-    with pytest.raises(NotImplementedError):
-        cfm(mu, torch.ones(2, 1, 10).cuda(), 2, spks=torch.zeros(2, 80).cuda(), streaming=True)
+    # T <= chunk: the streaming chunk mask is a no-op (one chunk covers every key)
+    a, _ = cfm(mu, torch.ones(2, 1, 10).cuda(), 2, spks=torch.zeros(2, 80).cuda(), streaming=True)
+    b, _ = cfm(mu, torch.ones(2, 1, 10).cuda(), 2, spks=torch.zeros(2, 80).cuda(), streaming=False)
+    assert torch.equal(a, b)
 
 
 # ------------------------------------------------------------------------------ HiFT

@@ -36,6 +36,24 @@ def test_estimator_forward_golden(est_sd):
     assert float(v[1, :, 20:].abs().max()) == 0.0
 
 
+def test_streaming_golden(est_sd, noise_bank):
+    """streaming=True: static chunk mask (chunk 50) in every attention (decoder.py:950-953, mask.py:91-126)."""
+    g = np.load(os.path.join(GOLDEN, "estimator_fwd_stream.npz"))
+    x, mask, mu, t, spks, cond = est_inputs(int(g["seed"]), int(g["R"]), int(g["T"]), list(g["lens"]))
+    with torch.no_grad():
+        v = oe.estimator_forward(est_sd, x, mask, mu, t, spks, cond, chunk=50)
+        v_full = oe.estimator_forward(est_sd, x, mask, mu, t, spks, cond)
+    ref = torch.from_numpy(g["out"])
+    assert (v - ref).abs().max().item() <= 2e-5
+    assert (v_full - ref).abs().max().item() > 1e-2  # the chunk mask matters at T = 120
+    g = np.load(os.path.join(GOLDEN, "cfm_T130_n3_stream.npz"))
+    T, n = int(g["T"]), int(g["n_timesteps"])
+    mu, spks = cfm_inputs(int(g["seed"]), T)
+    with torch.no_grad():
+        mel = oe.cfm_forward(est_sd, noise_bank, mu, torch.ones(1, 1, T), n, 1.0, spks, torch.zeros(1, 80, T), chunk=50)
+    assert (mel - torch.from_numpy(g["out"])).abs().max().item() <= 1e-4
+
+
 @pytest.mark.parametrize("name", ["cfm_T33_n4", "cfm_T50_n10"])
 def test_cfm_golden(est_sd, noise_bank, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
