@@ -177,6 +177,45 @@ def test_cfm_batch_invariance_full_size(cfms):
         assert torch.equal(one[0], mel[i, :, : lens[i]])
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_cfm_long_utterance_config4_shape(cfms, prec, est_sd, noise_bank):
+    """BASELINE config 4 shape: a 30 s utterance (T = 1500, 24 key tiles, attention = 57 % of the flops), against the
+    batch-1 oracle; one Euler step keeps the CPU side to seconds."""
+    from oracle import estimator as oe
+    T = 1500
+    g = torch.Generator().manual_seed(1500)
+    mu = torch.randn(1, 80, T, generator=g)
+    spks = torch.randn(1, 80, generator=g)
+    mel, _ = cfms[prec](mu.cuda(), None, 1, 1.0, spks.cuda(), None, lengths=[T])
+    with torch.no_grad():
+        ref = oe.cfm_forward(est_sd, noise_bank, mu, torch.ones(1, 1, T), 1, 1.0, spks, torch.zeros(1, 80, T))
+    err = (mel.cpu() - ref).abs().max().item()
+    if prec == "fp32":
+        assert err <= FP32_MEL_TOL
+    else:
+        assert err <= BF16_MEL_TOL and rel_rms(mel.cpu(), ref) <= BF16_MEL_RELRMS
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_streaming_ragged_vs_oracle(cfms, prec, est_sd):
+    """streaming=True on a ragged batch whose lengths straddle chunk (50) and key-tile (64) boundaries."""
+    from oracle import estimator as oe
+    from oracle.make_golden import est_inputs
+    lens = [330, 50, 129, 64, 51, 200]
+    x, mask, mu, t, spks, cond = est_inputs(33, len(lens), max(lens), lens)
+    v = cfms[prec].estimator(x.cuda(), mask.cuda(), mu.cuda(), t.cuda(), spks.cuda(), cond.cuda(), streaming=True).cpu()
+    with torch.no_grad():
+        ref = torch.zeros_like(v)
+        for i, l in enumerate(lens):  # the oracle on each utterance alone, unpadded
+            ref[i:i + 1, :, :l] = oe.estimator_forward(est_sd, x[i:i + 1, :, :l], mask[i:i + 1, :, :l], mu[i:i + 1, :, :l],
+                                                       t[i:i + 1], spks[i:i + 1], cond[i:i + 1, :, :l], chunk=50)
+    err = (v - ref).abs().max().item()
+    if prec == "fp32":
+        assert err <= 1e-4
+    else:
+        assert err <= BF16_MEL_TOL and rel_rms(v, ref) <= BF16_MEL_RELRMS
+
+
 def test_cfm_errors(cfms):
     cfm = cfms["fp32"]
     mu = torch.zeros(2, 80, 10).cuda()
