@@ -226,6 +226,15 @@ __global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict
                                                          float* __restrict__ wav, const IstftTables tb, float limit) {
   __shared__ float re[67][9];
   __shared__ float im[67][9];
+  // the synthesis tables are indexed by a per-lane sample phase j: from the constant bank (kernel parameter) that is a
+  // 16-way serialised access, from shared memory it is conflict-free
+  __shared__ float s_cr[9][16], s_ci[9][16], s_w2[16];
+  if (threadIdx.x < 144) {
+    s_cr[threadIdx.x >> 4][threadIdx.x & 15] = tb.cr[threadIdx.x >> 4][threadIdx.x & 15];
+    s_ci[threadIdx.x >> 4][threadIdx.x & 15] = tb.ci[threadIdx.x >> 4][threadIdx.x & 15];
+  } else if (threadIdx.x < 160) {
+    s_w2[threadIdx.x - 144] = tb.w2[threadIdx.x - 144];
+  }
   const int b = blockIdx.y;
   const int T = sq.len[b];
   const int n0 = blockIdx.x * 256;  // first output sample of this block
@@ -265,9 +274,9 @@ __global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict
       const int fi = f - f_lo;
       float v = 0.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) v = fmaf(re[fi][k], tb.cr[k][j], fmaf(im[fi][k], tb.ci[k][j], v));
+      for (int k = 0; k < 9; ++k) v = fmaf(re[fi][k], s_cr[k][j], fmaf(im[fi][k], s_ci[k][j], v));
       acc += v;
-      env += tb.w2[j];
+      env += s_w2[j];
     }
     y = acc / env;
     y = fminf(fmaxf(y, -limit), limit);
