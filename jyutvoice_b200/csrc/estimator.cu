@@ -7,6 +7,7 @@
 #include "engine.cuh"
 #include "kernels.cuh"
 #include "attention_tc.cuh"
+#include "mlp_tc.cuh"
 #include "weights.cuh"
 
 namespace jv {
@@ -304,6 +305,16 @@ static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void*
   e.gemm(g, c.st);
 }
 
+// JYUTVOICE_B200_MLP=0 falls back to the two-launch feed-forward (FF1 + GELU, FF2 + residual + norm)
+static bool use_mlp_fused() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_MLP");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // BasicTransformerBlock (transformer.py:355-443).  On entry LNX = norm1(X).  `next_ln`: norm1 of the following
 // block (fused into the FF2 epilogue) or null; `copy_to`: activation-typed copy of the block output (conv input).
 static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, void* copy_to) {
@@ -319,6 +330,13 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g.x_bf16 = g.x_in_half = g.x_out_half = xb;
   set_ln2(c, g, w.n3);
   e.gemm(g, c.st);
+  if (xb && use_mlp_fused()) {  // FF1 + GELU + FF2 + residual (+ next norm1) in one kernel: the hidden never leaves the SM
+    const bool to_copy = copy_to != nullptr;
+    launch_mlp_fused(e.tmaps, c.b.LNX, w.ff1.W, w.ff1.bias, w.ff2.W, w.ff2.bias, c.b.X, to_copy ? copy_to : c.b.X, to_copy ? 0 : 1,
+                     next_ln ? next_ln->g : nullptr, next_ln ? next_ln->b : nullptr, next_ln ? c.b.LNX : nullptr, c.b.frame_row,
+                     c.M_alloc, e.num_sms, 2.0 * (double)c.valid_frames * (2.0 * C * 1024), c.st);
+    return;
+  }
   g = conv_desc(c, w.ff1, c.b.LNX, nullptr, 1);
   g.act = ACT_GELU;
   g.out_act = c.b.FF; g.ldo2 = 1024;

@@ -216,6 +216,32 @@ def test_streaming_ragged_vs_oracle(cfms, prec, est_sd):
         assert err <= BF16_MEL_TOL and rel_rms(v, ref) <= BF16_MEL_RELRMS
 
 
+def test_fused_mlp_experimental_path():
+    """JYUTVOICE_B200_MLP=1 (opt-in): FF1 + GELU + FF2 + residual + norm in one tcgen05 kernel (csrc/mlp_tc.cuh).  The
+    switch is read once per process, hence the subprocess; same golden, same bf16 gate."""
+    import subprocess
+    import sys
+    code = (
+        "import os, numpy as np, torch\n"
+        "from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, synthetic\n"
+        "from oracle.make_golden import est_inputs\n"
+        "g = np.load(os.path.join('tests', 'golden', 'estimator_fwd.npz'))\n"
+        "cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision='bf16'))\n"
+        "cfm.load_state_dict(synthetic.make_estimator_state_dict(), strict=True)\n"
+        "cfm = cfm.cuda()\n"
+        "a = [z.cuda() for z in est_inputs(int(g['seed']), int(g['R']), int(g['T']), list(g['lens']))]\n"
+        "v = cfm.estimator(*a).cpu()\n"
+        "ref = torch.from_numpy(g['out'])\n"
+        "print('ERR', float((v - ref).abs().max()), float((v - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()))\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JYUTVOICE_B200_MLP="1", PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    err, rel = [float(z) for z in out.stdout.split("ERR")[1].split()[:2]]
+    assert err <= BF16_MEL_TOL and rel <= BF16_MEL_RELRMS
+
+
 def test_cfm_errors(cfms):
     cfm = cfms["fp32"]
     mu = torch.zeros(2, 80, 10).cuda()
