@@ -45,6 +45,10 @@ int jv_version(void);
 const char* jv_last_error(void);
 /* Number of kernel launches this library has enqueued in this process (bench.py's gpu_launches). */
 uint64_t jv_launch_count(void);
+/* CUDA-graph replays issued by jv_cfm_solve so far (one replay = one Euler step = ~330 kernels, all of them counted in
+ * jv_launch_count).  Step 0 of a solve runs eagerly, step 1 is captured, steps 1 .. n-1 replay it; JYUTVOICE_B200_GRAPH=0
+ * or a failed capture falls back to eager launches. */
+uint64_t jv_graph_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Estimator = CausalConditionalDecoder (jyutvoice/flow/decoder.py:798-1018) with the

@@ -4,6 +4,7 @@
 namespace jv {
 static thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launch_count{0};
+std::atomic<uint64_t> g_graph_launches{0};
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 __global__ void cvt_f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long n) {
@@ -19,6 +20,7 @@ extern "C" {
 int jv_version(void) { return 1; }
 const char* jv_last_error(void) { return g_last_error.c_str(); }
 uint64_t jv_launch_count(void) { return g_launch_count.load(); }
+uint64_t jv_graph_launch_count(void) { return g_graph_launches.load(); }
 
 int jv_profile_begin(void) {
   JV_API_BEGIN

@@ -26,6 +26,7 @@ struct Error : public std::runtime_error {
 
 void set_last_error(const std::string& msg);
 extern std::atomic<uint64_t> g_launch_count;
+extern std::atomic<uint64_t> g_graph_launches;  // CUDA-graph replays of an Euler step (jv_cfm_solve)
 
 #define JV_CUDA(expr)                                                                              \
   do {                                                                                             \

@@ -44,6 +44,7 @@ struct jv_estimator {
   DeviceAlloc mem;
   bool finalized = false;
   int chunk = 0;  // attention chunk mask of streaming=True (decoder.py:950-953); 0 = full context
+  cudaStream_t cap_stream = nullptr;  // private stream used only to capture one Euler step into a CUDA graph
   GroupW groups[N_RESNET];  // 0 = down, 1..12 = mid, 13 = up
   PackedW down_conv, up_conv, final_conv, final_proj;
   LNW final_ln;
@@ -353,6 +354,16 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   e.gemm(g, c.st);
 }
 
+// JYUTVOICE_B200_GRAPH=0: every Euler step is launched eagerly
+static bool use_graph() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_GRAPH");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // A0 (packed [M,320]) -> V (fp32 [M,80], masked)
 static void forward_packed(const FwdCtx& c) {
   jv_estimator* h = c.h;
@@ -439,11 +450,40 @@ static void run_pack(const FwdCtx& c, const float* x, const float* mu, const flo
   else launch_pack<float>(c, x, mu, spks, cond, Tmax, cfg);
 }
 
+// Capture one Euler step (issued on the handle's private capture stream: the caller's stream may be the legacy default
+// stream, which cannot be captured) into an executable graph.  Any failure ends the capture and returns false: the
+// caller falls back to eager launches.
+template <typename F>
+static bool capture_step(jv_estimator* h, FwdCtx& c, F&& step, cudaGraphExec_t* exec) {
+  if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  c.st = h->cap_stream;
+  bool ok = true;
+  try {
+    step();
+  } catch (const std::exception&) {
+    ok = false;
+  }
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamEndCapture(h->cap_stream, &graph) != cudaSuccess || !graph) ok = false;
+  if (ok && cudaGraphInstantiate(exec, graph, 0) != cudaSuccess) ok = false;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) cudaGetLastError();
+  return ok;
+}
+
 static size_t workspace_bytes(const jv_estimator* h, int R, const int32_t* lens, int nt) {
   EstLayout L = make_layout(R, lens);
   Arena ar(nullptr, 0);
   carve(ar, h->eng, L.M_alloc, R, nt);
   ar.alloc<int>(R);  // lens copy (solver)
+  ar.alloc<float>(64);  // Euler step sizes (solver)
   return ar.off + 256;
 }
 
@@ -463,7 +503,10 @@ int jv_estimator_create(int device, int precision, jv_estimator** out) {
   JV_API_END
 }
 
-void jv_estimator_destroy(jv_estimator* h) { delete h; }
+void jv_estimator_destroy(jv_estimator* h) {
+  if (h && h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  delete h;
+}
 
 int jv_estimator_set_chunk(jv_estimator* h, int chunk_size) {
   JV_API_BEGIN
@@ -570,6 +613,7 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
   c.h = h;
   c.b = carve(ar, h->eng, L.M_alloc, R, 64);
   int* lens_dev = ar.alloc<int>(R);
+  float* dts_dev = ar.alloc<float>(64);
   c.M = L.M; c.M_alloc = L.M_alloc; c.R = R; c.Tmax_len = tmax_len;
   c.valid_frames = 0;
   for (int r = 0; r < R; ++r) c.valid_frames += L.row_len[r];
@@ -590,17 +634,47 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
       if (k < n_timesteps) dt = t_span_host[k + 1] - t;
     }
   }
+  JV_CUDA(cudaMemcpyAsync(dts_dev, dts.data(), n_timesteps * sizeof(float), cudaMemcpyHostToDevice, c.st));
+  JV_CUDA(cudaStreamSynchronize(c.st));  // dts dies with this frame
   run_time_embedding(c, ts.data(), n_timesteps);  // all steps at once: temb depends on t only
   const long nx = (long)B * 80 * Tmax;
   init_noise_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, c.st>>>(out_mel, noise, noise_stride, lens_dev, B, Tmax, temperature);
   JV_LAUNCHED();
-  for (int k = 0; k < n_timesteps; ++k) {
-    c.temb_step = c.b.temb + (size_t)k * N_RESNET * C;  // every row of step k shares t_k (row_tidx == 0)
+  // One Euler step = pack, estimator forward (~330 launches), CFG + update, advance.  What differs between steps (the
+  // time-embedding row and dt) is selected on the device through row_tidx (= step index for every row), so the launch
+  // sequence is identical for all steps: step 0 runs eagerly, step 1 is captured into a CUDA graph, steps 1 .. n-1 replay it.
+  const cudaStream_t user_st = c.st;
+  auto euler_step = [&]() {
     run_pack(c, out_mel, mu, spks, cond, Tmax, 1);
     forward_packed(c);
-    cfg_euler_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, c.st>>>(out_mel, c.b.V, 80, c.b.row_off, lens_dev, B, Tmax, dts[k], cfg_rate);
+    cfg_euler_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, c.st>>>(out_mel, c.b.V, 80, c.b.row_off, lens_dev, B, Tmax, dts_dev,
+                                                                     c.b.row_tidx, cfg_rate);
     JV_LAUNCHED();
+    step_advance_kernel<<<cdiv(R, 256), 256, 0, c.st>>>(c.b.row_tidx, R);
+    JV_LAUNCHED();
+  };
+  euler_step();
+  int k = 1;
+  if (n_timesteps >= 3 && use_graph() && !profile_state().on) {
+    cudaGraphExec_t exec = nullptr;
+    const uint64_t before = g_launch_count.load();
+    const bool captured = capture_step(h, c, euler_step, &exec);
+    const uint64_t nodes = g_launch_count.load() - before;
+    g_launch_count.fetch_sub(nodes);  // a captured launch does not run; every replay runs `nodes` kernels
+    if (captured) {
+      c.st = user_st;
+      cudaError_t rc = cudaSuccess;
+      for (; k < n_timesteps && rc == cudaSuccess; ++k) {
+        rc = cudaGraphLaunch(exec, user_st);
+        g_launch_count.fetch_add(nodes);
+        g_graph_launches.fetch_add(1);
+      }
+      cudaGraphExecDestroy(exec);  // launches are asynchronous: the runtime defers the destruction until they have run
+      JV_CUDA(rc);
+    }
+    c.st = user_st;
   }
+  for (; k < n_timesteps; ++k) euler_step();
   JV_API_END
 }
 

@@ -50,10 +50,14 @@ __global__ void init_noise_kernel(float* __restrict__ x, const float* __restrict
 }
 
 // x[b,c,t] += dt * ((1+cfg) * v[row 2b] - cfg * v[row 2b+1])   (flow_matching.py:255-259)
+// dt = dts[step[0]]: the Euler step index lives on the device (row_tidx of the solver), so one captured launch sequence
+// serves every step of the solve.
 __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ v, int ldv, const int* __restrict__ row_off,
-                                 const int* __restrict__ lens, int B, int Tmax, float dt, float cfg) {
+                                 const int* __restrict__ lens, int B, int Tmax, const float* __restrict__ dts,
+                                 const int* __restrict__ step, float cfg) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * 80 * Tmax) return;
+  const float dt = dts[step[0]];
   int t = (int)(idx % Tmax);
   int c = (int)((idx / Tmax) % 80);
   int b = (int)(idx / ((long)Tmax * 80));
@@ -62,6 +66,12 @@ __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict_
   float vu = v[(long)(row_off[2 * b + 1] + t) * ldv + c];
   float d = (1.0f + cfg) * vc - cfg * vu;
   x[idx] = x[idx] + dt * d;
+}
+
+// next Euler step: every estimator row moves on to the time-embedding row of step k + 1
+__global__ void step_advance_kernel(int* __restrict__ row_tidx, int R) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) row_tidx[i] += 1;
 }
 
 // out[r, c, t] = v[row_off[r] + t, c] for t < len_r else 0

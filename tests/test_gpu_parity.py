@@ -242,6 +242,27 @@ def test_fused_mlp_experimental_path():
     assert err <= BF16_MEL_TOL and rel <= BF16_MEL_RELRMS
 
 
+def test_cfm_solve_replays_a_graph_and_matches_eager_counts(cfms):
+    """Steps 1 .. n-1 of a solve replay one captured Euler step; the kernel-launch counter stays what eager gives."""
+    from jyutvoice_b200 import _lib
+    L = _lib.lib()
+    cfm = cfms["bf16"]
+    mu = torch.randn(2, 80, 40, generator=torch.Generator().manual_seed(4)).cuda()
+    spks = torch.zeros(2, 80).cuda()
+    cfm(mu, None, 2, spks=spks, lengths=[40, 33])  # n < 3: eager
+    g0, l0 = L.jv_graph_launch_count(), L.jv_launch_count()
+    cfm(mu, None, 2, spks=spks, lengths=[40, 33])
+    per2 = L.jv_launch_count() - l0
+    assert L.jv_graph_launch_count() == g0
+    l1 = L.jv_launch_count()
+    cfm(mu, None, 6, spks=spks, lengths=[40, 33])
+    per6 = L.jv_launch_count() - l1
+    if os.environ.get("JYUTVOICE_B200_GRAPH", "1") != "0":
+        assert L.jv_graph_launch_count() == g0 + 5
+    per_step = (per6 - per2) // 4
+    assert per_step > 300 and (per6 - per2) % 4 == 0  # four more Euler steps, each the same ~330 launches
+
+
 def test_cfm_errors(cfms):
     cfm = cfms["fp32"]
     mu = torch.zeros(2, 80, 10).cuda()
