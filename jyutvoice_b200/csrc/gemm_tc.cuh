@@ -433,6 +433,13 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   __syncthreads();
   if (csz > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
+  if (warp == 0 && lane == 0 && wres && unit0 < p.num_units) {
+    // The resident weight tile of this CTA's n-tile does not depend on the previous kernel: its 64-128 KB load runs
+    // while that kernel drains (a CTA that starts on an SM the previous grid has already left sits in pdl_wait anyway).
+    mbar_expect_tx(wres_bar, (uint32_t)k_iters * p.block_n * BLOCK_K * 2);
+    for (int it = 0; it < k_iters; ++it)
+      tma_load_2d(&tm.w, wres_bar, smem_b + it * p.b_stage_bytes, it * BLOCK_K, tile_n0(unit0));
+  }
   pdl_wait();  // from here on the previous kernel's results (activations, residual stream) may be read / overwritten
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -448,11 +455,6 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const uint32_t tx_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
       const bool slab = p.slab != 0;
       const int b_rows = p.block_n / csz;  // weight rows this CTA fetches (and multicasts)
-      if (wres && unit0 < p.num_units) {   // the whole weight tile of this CTA's n-tile, once
-        mbar_expect_tx(wres_bar, (uint32_t)k_iters * p.block_n * BLOCK_K * 2);
-        for (int it = 0; it < k_iters; ++it)
-          tma_load_2d(&tm.w, wres_bar, smem_b + it * p.b_stage_bytes, it * BLOCK_K, tile_n0(unit0));
-      }
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         const int m0 = tile_m0(unit);
         const int n0 = tile_n0(unit);
