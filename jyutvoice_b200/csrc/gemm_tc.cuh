@@ -443,8 +443,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   pdl_wait();  // from here on the previous kernel's results (activations, residual stream) may be read / overwritten
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // Register re-partitioning (general kernels, 384 threads): the producer / MMA / allocator warpgroup keeps 40 registers,
-  // the two epilogue warpgroups grow to 232, which lets the compiler interleave the 32 independent element chains of a chunk.
+  // Register re-partitioning (general kernels, 384 threads x 168 registers): the producer / MMA / allocator warpgroup
+  // drops to 80 registers, the two epilogue warpgroups grow to 208 (128 x 80 + 256 x 208 <= 384 x 168; a larger request
+  // would block in setmaxnreg.inc for ever).  setmaxnreg sits inside the role branches so that ptxas allocates per role.
   if (warp < 4) {
   if (N_EPI_WARPS == EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   if (warp == 0) {
