@@ -44,7 +44,9 @@ struct jv_estimator {
   DeviceAlloc mem;
   bool finalized = false;
   int chunk = 0;  // attention chunk mask of streaming=True (decoder.py:950-953); 0 = full context
-  cudaStream_t cap_stream = nullptr;  // private stream used only to capture one Euler step into a CUDA graph
+  cudaStream_t cap_stream = nullptr, cap_stream2 = nullptr;  // private streams used only to capture an Euler step into a CUDA graph
+  cudaStream_t aux_stream = nullptr;                         // second half-batch of a split solve (eager steps)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   GroupW groups[N_RESNET];  // 0 = down, 1..12 = mid, 13 = up
   PackedW down_conv, up_conv, final_conv, final_proj;
   LNW final_ln;
@@ -450,32 +452,60 @@ static void run_pack(const FwdCtx& c, const float* x, const float* mu, const flo
   else launch_pack<float>(c, x, mu, spks, cond, Tmax, cfg);
 }
 
-// Capture one Euler step (issued on the handle's private capture stream: the caller's stream may be the legacy default
-// stream, which cannot be captured) into an executable graph.  Any failure ends the capture and returns false: the
-// caller falls back to eager launches.
-template <typename F>
-static bool capture_step(jv_estimator* h, FwdCtx& c, F&& step, cudaGraphExec_t* exec) {
-  if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
+// JYUTVOICE_B200_SPLIT=1 (opt-in): a large solve runs as two concurrent half-batches.  Measured on B200 (batch 64 x 300,
+// same box, alternating runs): 2396 / 2400 audio-s/s unsplit against 2306 / 2311 split — the kernels' fixed costs
+// (prologue, resident weight loads, pipeline fill) double while the tail overlap recovers less than that.
+static bool use_split() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_SPLIT");
+    v = (e && e[0] == '1') ? 1 : 0;
   }
-  if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
+  return v == 1;
+}
+
+// A solve over B utterances may run as two independent half-batches on two streams: utterances do not interact, and
+// a grid of one persistent CTA per SM leaves most SMs idle while its last partial wave finishes (302 m-tiles on 148
+// SMs = 2.04 waves: a third round on six SMs).  With two chains the other half's next kernel takes the freed SMs.
+// Returns the first utterance of the second part (0 = no split).  Only when each half still fills the machine.
+static int plan_split(int B, const int32_t* lens, int num_sms) {
+  if (!use_split() || B < 2) return 0;
+  long total = 0;
+  for (int b = 0; b < B; ++b) total += 2L * (lens[b] + EST_GAP);
+  if (total < 2L * num_sms * 128) return 0;
+  long acc = 0;
+  for (int b = 0; b < B - 1; ++b) {
+    acc += 2L * (lens[b] + EST_GAP);
+    if (2 * acc >= total) return b + 1;
   }
-  c.st = h->cap_stream;
-  bool ok = true;
-  try {
-    step();
-  } catch (const std::exception&) {
-    ok = false;
+  return B - 1;
+}
+
+struct SolvePart {
+  int b0 = 0, B = 0;
+  FwdCtx c;
+  int* lens_dev = nullptr;
+  float* dts_dev = nullptr;
+};
+
+static void carve_part(SolvePart& pt, jv_estimator* h, Arena& ar, const int32_t* lens_host, int* tmax_len, EstLayout* Lout) {
+  const int R = 2 * pt.B;
+  std::vector<int32_t> l2(R);
+  int tl = 0;
+  for (int b = 0; b < pt.B; ++b) {
+    l2[2 * b] = l2[2 * b + 1] = lens_host[pt.b0 + b];
+    tl = std::max(tl, lens_host[pt.b0 + b]);
   }
-  cudaGraph_t graph = nullptr;
-  if (cudaStreamEndCapture(h->cap_stream, &graph) != cudaSuccess || !graph) ok = false;
-  if (ok && cudaGraphInstantiate(exec, graph, 0) != cudaSuccess) ok = false;
-  if (graph) cudaGraphDestroy(graph);
-  if (!ok) cudaGetLastError();
-  return ok;
+  EstLayout L = make_layout(R, l2.data());
+  pt.c.h = h;
+  pt.c.b = carve(ar, h->eng, L.M_alloc, R, 64);
+  pt.lens_dev = ar.alloc<int>(R);
+  pt.dts_dev = ar.alloc<float>(64);
+  pt.c.M = L.M; pt.c.M_alloc = L.M_alloc; pt.c.R = R; pt.c.Tmax_len = tl;
+  pt.c.valid_frames = 0;
+  for (int r = 0; r < R; ++r) pt.c.valid_frames += L.row_len[r];
+  if (tmax_len) *tmax_len = tl;
+  if (Lout) *Lout = std::move(L);
 }
 
 static size_t workspace_bytes(const jv_estimator* h, int R, const int32_t* lens, int nt) {
@@ -483,8 +513,26 @@ static size_t workspace_bytes(const jv_estimator* h, int R, const int32_t* lens,
   Arena ar(nullptr, 0);
   carve(ar, h->eng, L.M_alloc, R, nt);
   ar.alloc<int>(R);  // lens copy (solver)
-  ar.alloc<float>(64);  // Euler step sizes (solver)
   return ar.off + 256;
+}
+
+static size_t solve_workspace_bytes(jv_estimator* h, int B, const int32_t* lens_host) {
+  Arena ar(nullptr, 0);
+  const int bs = plan_split(B, lens_host, h->eng.num_sms);
+  SolvePart parts[2];
+  const int n_parts = bs ? 2 : 1;
+  parts[0].b0 = 0; parts[0].B = bs ? bs : B;
+  parts[1].b0 = bs; parts[1].B = B - bs;
+  for (int i = 0; i < n_parts; ++i) carve_part(parts[i], h, ar, lens_host, nullptr, nullptr);
+  size_t need = ar.off;
+  if (n_parts == 2) {  // the unsplit plan (used while profiling) must fit as well
+    Arena one(nullptr, 0);
+    SolvePart whole;
+    whole.b0 = 0; whole.B = B;
+    carve_part(whole, h, one, lens_host, nullptr, nullptr);
+    need = std::max(need, one.off);
+  }
+  return need + 256;
 }
 
 }  // namespace jv
@@ -504,7 +552,13 @@ int jv_estimator_create(int device, int precision, jv_estimator** out) {
 }
 
 void jv_estimator_destroy(jv_estimator* h) {
-  if (h && h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h) {
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->cap_stream2) cudaStreamDestroy(h->cap_stream2);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+  }
   delete h;
 }
 
@@ -544,9 +598,9 @@ size_t jv_cfm_workspace_bytes(const jv_estimator* h, int n_rows, const int32_t* 
 size_t jv_cfm_solve_workspace_bytes(const jv_estimator* h, int B, const int32_t* lens_host) {
   try {
     if (!h || B < 1 || !lens_host) return 0;
-    std::vector<int32_t> l2(2 * (size_t)B);
-    for (int b = 0; b < B; ++b) l2[2 * b] = l2[2 * b + 1] = lens_host[b];
-    return workspace_bytes(h, 2 * B, l2.data(), 64);
+    for (int b = 0; b < B; ++b)
+      if (lens_host[b] < 1) return 0;
+    return solve_workspace_bytes(const_cast<jv_estimator*>(h), B, lens_host);
   } catch (const std::exception& e) {
     jv::set_last_error(e.what());
     return 0;
@@ -597,31 +651,12 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
   JV_REQUIRE(B >= 1 && Tmax >= 1 && lens_host && mu && spks && noise && t_span_host && out_mel && ws, JV_ERR_INVALID, "bad arguments");
   JV_REQUIRE(n_timesteps >= 1 && n_timesteps <= 64, JV_ERR_INVALID, "n_timesteps = %d out of range [1, 64]", n_timesteps);
   JV_CUDA(cudaSetDevice(h->eng.device));
-  const int R = 2 * B;
-  std::vector<int32_t> l2(R);
-  int tmax_len = 0;
   for (int b = 0; b < B; ++b) {
     JV_REQUIRE(lens_host[b] >= 1 && lens_host[b] <= Tmax, JV_ERR_INVALID, "lens[%d] = %d outside [1, Tmax = %d]", b, lens_host[b], Tmax);
     JV_REQUIRE(lens_host[b] <= noise_stride, JV_ERR_INVALID, "lens[%d] = %d exceeds the noise bank (%lld frames)", b, lens_host[b],
                (long long)noise_stride);
-    l2[2 * b] = l2[2 * b + 1] = lens_host[b];
-    tmax_len = std::max(tmax_len, lens_host[b]);
   }
-  EstLayout L = make_layout(R, l2.data());
-  Arena ar(ws, ws_bytes);
-  FwdCtx c;
-  c.h = h;
-  c.b = carve(ar, h->eng, L.M_alloc, R, 64);
-  int* lens_dev = ar.alloc<int>(R);
-  float* dts_dev = ar.alloc<float>(64);
-  c.M = L.M; c.M_alloc = L.M_alloc; c.R = R; c.Tmax_len = tmax_len;
-  c.valid_frames = 0;
-  for (int r = 0; r < R; ++r) c.valid_frames += L.row_len[r];
-  c.st = (cudaStream_t)stream;
-  c.temb_step = c.b.temb;
-  std::vector<int> tidx(R, 0);
-  JV_CUDA(cudaMemcpyAsync(lens_dev, lens_host, B * sizeof(int), cudaMemcpyHostToDevice, c.st));
-  upload_layout(c, L, tidx);
+  const cudaStream_t user_st = (cudaStream_t)stream;
   // Euler bookkeeping exactly as flow_matching.py:230-263 (t and dt accumulate in fp32)
   std::vector<float> ts(n_timesteps), dts(n_timesteps);
   {
@@ -634,35 +669,104 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
       if (k < n_timesteps) dt = t_span_host[k + 1] - t;
     }
   }
-  JV_CUDA(cudaMemcpyAsync(dts_dev, dts.data(), n_timesteps * sizeof(float), cudaMemcpyHostToDevice, c.st));
-  JV_CUDA(cudaStreamSynchronize(c.st));  // dts dies with this frame
-  run_time_embedding(c, ts.data(), n_timesteps);  // all steps at once: temb depends on t only
-  const long nx = (long)B * 80 * Tmax;
-  init_noise_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, c.st>>>(out_mel, noise, noise_stride, lens_dev, B, Tmax, temperature);
-  JV_LAUNCHED();
-  // One Euler step = pack, estimator forward (~330 launches), CFG + update, advance.  What differs between steps (the
-  // time-embedding row and dt) is selected on the device through row_tidx (= step index for every row), so the launch
-  // sequence is identical for all steps: step 0 runs eagerly, step 1 is captured into a CUDA graph, steps 1 .. n-1 replay it.
-  const cudaStream_t user_st = c.st;
-  auto euler_step = [&]() {
-    run_pack(c, out_mel, mu, spks, cond, Tmax, 1);
+  // one or two independent half-batches (plan_split)
+  // (not while per-launch events are being recorded: a kernel's duration would include waiting for the other chain's SMs)
+  const int bs = profile_state().on ? 0 : plan_split(B, lens_host, h->eng.num_sms);
+  const int n_parts = bs ? 2 : 1;
+  SolvePart parts[2];
+  parts[0].b0 = 0; parts[0].B = bs ? bs : B;
+  parts[1].b0 = bs; parts[1].B = B - bs;
+  Arena ar(ws, ws_bytes);
+  for (int i = 0; i < n_parts; ++i) {  // set-up of both parts on the caller's stream
+    SolvePart& pt = parts[i];
+    EstLayout L;
+    carve_part(pt, h, ar, lens_host, nullptr, &L);
+    pt.c.st = user_st;
+    pt.c.temb_step = pt.c.b.temb;
+    std::vector<int> tidx(pt.c.R, 0);
+    JV_CUDA(cudaMemcpyAsync(pt.lens_dev, lens_host + pt.b0, pt.B * sizeof(int), cudaMemcpyHostToDevice, user_st));
+    JV_CUDA(cudaMemcpyAsync(pt.dts_dev, dts.data(), n_timesteps * sizeof(float), cudaMemcpyHostToDevice, user_st));
+    upload_layout(pt.c, L, tidx);                      // synchronises: the host vectors die with this frame
+    run_time_embedding(pt.c, ts.data(), n_timesteps);  // all steps at once: temb depends on t only
+  }
+  auto part_ptr = [&](const float* base, const SolvePart& pt, long per_utt) { return base ? base + (long)pt.b0 * per_utt : nullptr; };
+  // One Euler step of one part = pack, estimator forward (~330 launches), CFG + update, advance.  What differs between
+  // steps (the time-embedding row and dt) is selected on the device through row_tidx (= step index for every row), so
+  // the launch sequence is identical for all steps: step 0 runs eagerly, step 1 is captured into a CUDA graph (both
+  // parts as two branches), steps 1 .. n-1 replay it.
+  auto euler_step = [&](SolvePart& pt) {
+    FwdCtx& c = pt.c;
+    float* x = out_mel + (long)pt.b0 * 80 * Tmax;
+    const long nx = (long)pt.B * 80 * Tmax;
+    run_pack(c, x, part_ptr(mu, pt, 80L * Tmax), part_ptr(spks, pt, 80), part_ptr(cond, pt, 80L * Tmax), Tmax, 1);
     forward_packed(c);
-    cfg_euler_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, c.st>>>(out_mel, c.b.V, 80, c.b.row_off, lens_dev, B, Tmax, dts_dev,
+    cfg_euler_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, c.st>>>(x, c.b.V, 80, c.b.row_off, pt.lens_dev, pt.B, Tmax, pt.dts_dev,
                                                                      c.b.row_tidx, cfg_rate);
     JV_LAUNCHED();
-    step_advance_kernel<<<cdiv(R, 256), 256, 0, c.st>>>(c.b.row_tidx, R);
+    step_advance_kernel<<<cdiv(c.R, 256), 256, 0, c.st>>>(c.b.row_tidx, c.R);
     JV_LAUNCHED();
   };
-  euler_step();
+  // fork: part 1 runs on the handle's auxiliary stream
+  if (n_parts == 2) {
+    if (!h->aux_stream) JV_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    if (!h->ev_fork) JV_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    if (!h->ev_join) JV_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    JV_CUDA(cudaEventRecord(h->ev_fork, user_st));
+    JV_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+    parts[1].c.st = h->aux_stream;
+  }
+  for (int i = 0; i < n_parts; ++i) {
+    SolvePart& pt = parts[i];
+    const long nx = (long)pt.B * 80 * Tmax;
+    init_noise_kernel<<<(unsigned)((nx + 255) / 256), 256, 0, pt.c.st>>>(out_mel + (long)pt.b0 * 80 * Tmax, noise, noise_stride,
+                                                                          pt.lens_dev, pt.B, Tmax, temperature);
+    JV_LAUNCHED();
+    euler_step(pt);
+  }
+  auto join = [&]() {
+    if (n_parts == 2) {
+      JV_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+      JV_CUDA(cudaStreamWaitEvent(user_st, h->ev_join, 0));
+    }
+  };
   int k = 1;
   if (n_timesteps >= 3 && use_graph() && !profile_state().on) {
+    join();  // the graph is launched on the caller's stream only
     cudaGraphExec_t exec = nullptr;
     const uint64_t before = g_launch_count.load();
-    const bool captured = capture_step(h, c, euler_step, &exec);
+    bool captured = false;
+    do {  // capture one step of every part: the parts are branches forked from / joined into the capture origin
+      if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) break;
+      if (n_parts == 2 && !h->cap_stream2 && cudaStreamCreateWithFlags(&h->cap_stream2, cudaStreamNonBlocking) != cudaSuccess) break;
+      if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
+      bool ok = true;
+      try {
+        if (n_parts == 2) {
+          JV_CUDA(cudaEventRecord(h->ev_fork, h->cap_stream));
+          JV_CUDA(cudaStreamWaitEvent(h->cap_stream2, h->ev_fork, 0));
+        }
+        for (int i = 0; i < n_parts; ++i) {
+          parts[i].c.st = i == 0 ? h->cap_stream : h->cap_stream2;
+          euler_step(parts[i]);
+        }
+        if (n_parts == 2) {
+          JV_CUDA(cudaEventRecord(h->ev_join, h->cap_stream2));
+          JV_CUDA(cudaStreamWaitEvent(h->cap_stream, h->ev_join, 0));
+        }
+      } catch (const std::exception&) {
+        ok = false;
+      }
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamEndCapture(h->cap_stream, &graph) != cudaSuccess || !graph) ok = false;
+      if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+      if (graph) cudaGraphDestroy(graph);
+      captured = ok;
+    } while (false);
+    if (!captured) cudaGetLastError();
     const uint64_t nodes = g_launch_count.load() - before;
     g_launch_count.fetch_sub(nodes);  // a captured launch does not run; every replay runs `nodes` kernels
+    parts[0].c.st = user_st;
     if (captured) {
-      c.st = user_st;
       cudaError_t rc = cudaSuccess;
       for (; k < n_timesteps && rc == cudaSuccess; ++k) {
         rc = cudaGraphLaunch(exec, user_st);
@@ -671,10 +775,21 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
       }
       cudaGraphExecDestroy(exec);  // launches are asynchronous: the runtime defers the destruction until they have run
       JV_CUDA(rc);
+      n_timesteps = k;  // nothing left for the eager loop; the parts are already joined
+      if (n_parts == 2) parts[1].c.st = user_st;
+    } else if (n_parts == 2) {  // eager fallback: fork again
+      JV_CUDA(cudaEventRecord(h->ev_fork, user_st));
+      JV_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+      parts[1].c.st = h->aux_stream;
     }
-    c.st = user_st;
   }
-  for (; k < n_timesteps; ++k) euler_step();
+  if (k < n_timesteps) {
+    for (; k < n_timesteps; ++k)
+      for (int i = 0; i < n_parts; ++i) euler_step(parts[i]);
+    join();
+  } else if (!(n_timesteps >= 3 && use_graph() && !profile_state().on)) {
+    join();
+  }
   JV_API_END
 }
 

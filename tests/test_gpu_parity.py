@@ -216,6 +216,33 @@ def test_streaming_ragged_vs_oracle(cfms, prec, est_sd):
         assert err <= BF16_MEL_TOL and rel_rms(v, ref) <= BF16_MEL_RELRMS
 
 
+def test_split_solve_experimental_path(est_sd, noise_bank):
+    """JYUTVOICE_B200_SPLIT=1 (opt-in): a large solve as two concurrent half-batches on two streams / graph branches must
+    give bit-identical mels to the default single chain (same kernels, same per-utterance arithmetic)."""
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, synthetic\n"
+        "cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision='bf16'))\n"
+        "cfm.load_state_dict(synthetic.make_estimator_state_dict(), strict=True)\n"
+        "cfm = cfm.cuda()\n"
+        "g = torch.Generator().manual_seed(9)\n"
+        "lens = [int(v) for v in torch.randint(270, 331, (64,), generator=g)]\n"
+        "mu = torch.randn(64, 80, 330, generator=g).cuda(); spks = torch.randn(64, 80, generator=g).cuda()\n"
+        "mel, _ = cfm(mu, None, 4, 1.0, spks, None, lengths=lens)\n"
+        "print('SUM', float(mel.double().sum()), float(mel.double().abs().sum()))\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for split in ("0", "1"):
+        env = dict(os.environ, JYUTVOICE_B200_SPLIT=split, PYTHONPATH=root)
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append(out.stdout.split("SUM")[1].split()[:2])
+    assert outs[0] == outs[1]
+
+
 def test_fused_mlp_experimental_path():
     """JYUTVOICE_B200_MLP=1 (opt-in): FF1 + GELU + FF2 + residual + norm in one tcgen05 kernel (csrc/mlp_tc.cuh).  The
     switch is read once per process, hence the subprocess; same golden, same bf16 gate."""
