@@ -147,6 +147,7 @@ static void finalize_impl(jv_estimator* h) {
   h->t_b2 = h->mem.upload_f32(h->store.get("time_mlp.linear_2.bias", {1024}).data);
   h->mlp_w = h->mem.upload_f32(mlp_w);
   h->mlp_b = h->mem.upload_f32(mlp_b);
+  h->store.require_all_used();  // names the first unexpected key (load_state_dict(strict=True) semantics)
   JV_REQUIRE(h->store.t.size() == 910, JV_ERR_STATE, "expected 910 estimator tensors, got %zu (unexpected keys present)",
              h->store.t.size());
   h->store.t.clear();

@@ -56,6 +56,17 @@ static int cluster_size() {  // CTAs per cluster for the weight multicast: 0 / 1
   return v;
 }
 
+// n-tile width of the N > 256 kernels (QKV, FF1): 256 unless JYUTVOICE_B200_BLOCKN overrides it (128 / 192 / 256 and N % it == 0)
+static int wide_block_n(int N) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_BLOCKN");
+    v = e ? atoi(e) : 256;
+    if (v != 128 && v != 192 && v != 256) v = 256;
+  }
+  return (N % v == 0) ? v : 256;
+}
+
 typedef void (*KernelFn)(const tc::TcMaps, const GemmDesc, const tc::TcParams);
 struct KernelEntry {
   int epi;
@@ -167,7 +178,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
     attr_set = true;
   }
   tc::TcParams p;
-  p.block_n = g.N <= 256 ? round_up(g.N, 32) : 256;
+  p.block_n = g.N <= 256 ? round_up(g.N, 32) : wide_block_n(g.N);
   p.n_tiles_n = cdiv(g.N, p.block_n);
   const int m_tiles = cdiv(g.M, tc::BLOCK_M);
   p.num_tiles = m_tiles * p.n_tiles_n;

@@ -176,6 +176,7 @@ static void hift_finalize_impl(jv_hift* h) {
       h->istft_tb.ci[k][n] = (k == 0 || k == 8) ? 0.f : (float)(-ck * std::sin(ang) / 16.0) * wf;
     }
   for (int n = 0; n < 16; ++n) h->istft_tb.w2[n] = (float)w[n] * (float)w[n];
+  h->store.require_all_used();  // names the first unexpected key (load_state_dict(strict=True) semantics)
   JV_REQUIRE(h->store.t.size() == 328, JV_ERR_STATE, "expected 328 HiFT tensors, got %zu (unexpected keys present)", h->store.t.size());
   h->store.t.clear();
   JV_CUDA(cudaDeviceSynchronize());

@@ -2,6 +2,7 @@
 // set_weight() keeps an fp32 host copy per reference state_dict key; finalize() packs them into the
 // K-major [N, taps*K_tap] slabs the GEMM engines read (fp32 or bf16) and uploads them once.
 #pragma once
+#include <set>
 #include "common.cuh"
 
 namespace jv {
@@ -27,9 +28,15 @@ struct WeightStore {
     JV_CUDA(cudaMemcpy(h.data.data(), data, n * sizeof(float), cudaMemcpyDefault));  // host or device source
     t[key] = std::move(h);
   }
+  mutable std::set<std::string> used;  // keys the architecture asked for (finalize: every stored key must be one of them)
+  // load_state_dict(strict=True) semantics: a key the architecture never reads is an error, not silently ignored
+  void require_all_used() const {
+    for (const auto& kv : t) JV_REQUIRE(used.count(kv.first) != 0, JV_ERR_INVALID, "unexpected weight '%s'", kv.first.c_str());
+  }
   const HostTensor& get(const std::string& key, std::initializer_list<int64_t> shape) const {
     auto it = t.find(key);
     JV_REQUIRE(it != t.end(), JV_ERR_STATE, "missing weight '%s'", key.c_str());
+    used.insert(key);
     const HostTensor& h = it->second;
     bool ok = h.shape.size() == shape.size();
     size_t i = 0;

@@ -290,6 +290,69 @@ def test_cfm_solve_replays_a_graph_and_matches_eager_counts(cfms):
     assert per_step > 300 and (per6 - per2) % 4 == 0  # four more Euler steps, each the same ~330 launches
 
 
+def test_c_abi_error_codes(cfms):
+    """Raw C-ABI calls: status codes and messages instead of exceptions / crashes (include/jyutvoice_b200.h)."""
+    from jyutvoice_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    h = cfms["fp32"].estimator.handle(dev)
+    T = 12
+    lens = _lib.i32_array([T])
+    mu = torch.zeros(1, 80, T, device=dev)
+    spks = torch.zeros(1, 80, device=dev)
+    noise = torch.zeros(80, 64, device=dev)
+    out = torch.empty(1, 80, T, device=dev)
+    tspan = _lib.f32_array([0.0, 0.5, 1.0])
+    p = lambda z: ctypes.c_void_p(z.data_ptr())
+    need = L.jv_cfm_solve_workspace_bytes(h, 1, lens)
+    assert need > 0
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+
+    def solve(hh, lens_, ws_bytes, n=2, noise_stride=64):
+        return L.jv_cfm_solve(hh, 1, T, lens_, p(mu), p(spks), None, p(noise), noise_stride, 1.0, n, tspan, 0.7, p(out), p(ws),
+                              ws_bytes, None)
+
+    assert solve(h, lens, need) == _lib.JV_OK
+    assert solve(h, lens, 1024) == _lib.JV_ERR_STATE and b"workspace too small" in L.jv_last_error()
+    assert solve(h, _lib.i32_array([T + 1]), need) == _lib.JV_ERR_INVALID and b"lens[0]" in L.jv_last_error()
+    assert solve(h, _lib.i32_array([0]), need) == _lib.JV_ERR_INVALID
+    assert solve(h, lens, need, n=0) == _lib.JV_ERR_INVALID
+    assert solve(h, lens, need, noise_stride=4) == _lib.JV_ERR_INVALID and b"noise bank" in L.jv_last_error()
+    assert solve(None, lens, need) == _lib.JV_ERR_STATE
+    assert L.jv_cfm_solve_workspace_bytes(None, 1, lens) == 0
+    assert L.jv_estimator_set_chunk(h, -1) == _lib.JV_ERR_INVALID
+    # a fresh handle with no weights: finalize names the first missing key, forward refuses to run
+    h2 = ctypes.c_void_p()
+    assert L.jv_estimator_create(0, _lib.PREC["fp32"], ctypes.byref(h2)) == _lib.JV_OK
+    try:
+        assert L.jv_estimator_finalize(h2) == _lib.JV_ERR_STATE and b"time_mlp" in L.jv_last_error() or b"missing" in L.jv_last_error()
+        assert solve(h2, lens, need) == _lib.JV_ERR_STATE
+        shape = (ctypes.c_int64 * 2)(3, 0)
+        w = torch.zeros(3, 3)
+        assert L.jv_estimator_set_weight(h2, b"x", ctypes.c_void_p(w.data_ptr()), shape, 2) == _lib.JV_ERR_INVALID  # empty dim
+        assert L.jv_estimator_set_weight(h2, None, ctypes.c_void_p(w.data_ptr()), shape, 2) == _lib.JV_ERR_INVALID
+    finally:
+        L.jv_estimator_destroy(h2)
+    assert solve(h, lens, need) == _lib.JV_OK  # the good handle is unaffected
+
+
+def test_finalize_is_strict_about_keys(est_sd):
+    """load_state_dict(strict=True) semantics at the C level: an extra key fails finalize and is named."""
+    from jyutvoice_b200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.jv_estimator_create(0, _lib.PREC["fp32"], ctypes.byref(h)) == _lib.JV_OK
+    try:
+        _lib.set_weights(h, L.jv_estimator_set_weight, [(k[len("estimator."):], v) for k, v in est_sd.items()])
+        extra = torch.zeros(4, 4)
+        shape = (ctypes.c_int64 * 2)(4, 4)
+        assert L.jv_estimator_set_weight(h, b"mid_blocks.0.1.0.attn1.to_q.lora", ctypes.c_void_p(extra.data_ptr()), shape, 2) == _lib.JV_OK
+        assert L.jv_estimator_finalize(h) != _lib.JV_OK
+        assert b"to_q.lora" in L.jv_last_error()
+    finally:
+        L.jv_estimator_destroy(h)
+
+
 def test_cfm_errors(cfms):
     cfm = cfms["fp32"]
     mu = torch.zeros(2, 80, 10).cuda()
