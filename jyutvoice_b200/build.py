@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "lib.cu")]
+    extra = os.environ.get("JYUTVOICE_B200_NVCC_FLAGS", "").split()  # experiments, e.g. -DJV_ATTN_POLY_EVERY=4
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "lib.cu")]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
