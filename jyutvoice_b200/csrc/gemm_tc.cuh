@@ -116,6 +116,31 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// tile flags (GemmDesc::flag_*): release increment after a tile's stores completed / acquire poll before a tile's loads
+__device__ __forceinline__ void flag_release_add(int* p) {
+  __threadfence();
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void flag_acquire_wait(const int* p, int target, int tag) {
+  int v;
+  long long t0 = 0;
+  uint32_t polls = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= target) break;
+    if ((++polls & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000LL) {
+        printf("jyutvoice_b200: tile flag wait timed out (tag %d, block %d, have %d, want %d)\n", tag, blockIdx.x, v, target);
+        __trap();
+      }
+    }
+  }
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");  // the TMA loads that follow read what the producer's TMA stores wrote
+}
+
 // Programmatic dependent launch: the prologue (barrier init, TMEM allocation, smem vector cache) runs while the
 // previous kernel in the stream drains; nothing produced by that kernel is touched before pdl_wait().
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -440,8 +465,12 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     for (int it = 0; it < k_iters; ++it)
       tma_load_2d(&tm.w, wres_bar, smem_b + it * p.b_stage_bytes, it * BLOCK_K, tile_n0(unit0));
   }
-  pdl_wait();  // from here on the previous kernel's results (activations, residual stream) may be read / overwritten
+  // from here on the previous kernel's results (activations, residual stream) may be read / overwritten — unless this
+  // launch consumes its A operand tile by tile through flags: then the grid-wide wait moves to the end of the kernel
+  // (it keeps "kernel n+2 waits for n+1, which waited for n" intact) and only the TMA producer waits, per m-tile.
+  if (!g.flag_in) pdl_wait();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const int flag_target = g.flag_in ? g.flag_warps * (g.flag_step[0] * g.flag_per_step + g.flag_base + 1) : 0;
 
   // Register re-partitioning (general kernels, 384 threads x 168 registers): the producer / MMA / allocator warpgroup
   // drops to 80 registers, the two epilogue warpgroups grow to 208 (128 x 80 + 256 x 208 <= 384 x 168; a larger request
@@ -459,6 +488,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         const int m0 = tile_m0(unit);
         const int n0 = tile_n0(unit);
+        if (g.flag_in) flag_acquire_wait(g.flag_in + m0 / BLOCK_M, flag_target, 7);
         if (slab) {  // one slab per 64-channel block, shared by all taps
           for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
@@ -583,6 +613,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     const int c_first = tile_par ? 0 : sub_id, c_step = tile_par ? 1 : N_SUB;
     int t_local = 0;   // tiles seen by this CTA
     uint32_t n_out = 0;  // output chunks staged by this warp (alternates the bf16 staging buffers)
+    int flag_pending = -1;  // m-tile whose stores were issued by this warp but not yet published through flag_out
     const int n_chunks = p.block_n >> 5;
     const float* smf = reinterpret_cast<const float*>(smem_raw + (base - raw));
     for (int unit = unit0; unit < p.num_units; unit += unit_step, ++t_local) {
@@ -601,6 +632,13 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const float* v_b2 = p.vec_ln2 ? smf + p.vec_ln2 / 4 + p.block_n - n0 : g.ln2_beta;
       const float* v_act = g.act_vec ? (p.vec_act ? smf + p.vec_act / 4 - n0 : g.act_vec) : nullptr;
       const float* v_act2 = g.act2_vec ? (p.vec_act2 ? smf + p.vec_act2 / 4 - n0 : g.act2_vec) : nullptr;
+      if (g.flag_out && flag_pending >= 0) {  // the previous tile's stores have had a whole mainloop to land
+        if (lane == 0) {
+          bulk_wait0();
+          flag_release_add(g.flag_out + flag_pending);
+        }
+        flag_pending = -1;
+      }
       if (XB) {  // residual of the first two chunks: in flight while the accumulator is still being computed
         if (lane == 0) {
           mbar_expect_tx(ebar, EPI_B16_BYTES);
@@ -796,9 +834,14 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * grp);
       if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
+      if (g.flag_out) flag_pending = m0 / BLOCK_M;
     }
-    if (lane == 0) bulk_wait0();  // smem must outlive the last TMA store's reads
+    if (lane == 0) {
+      bulk_wait0();  // smem must outlive the last TMA store's reads
+      if (g.flag_out && flag_pending >= 0) flag_release_add(g.flag_out + flag_pending);
+    }
   }
+  if (g.flag_in) pdl_wait();  // see above: every thread, after its role's work
 
   tc_fence_before();
   __syncthreads();
