@@ -232,6 +232,10 @@ struct GemmDesc {
   const int* flag_in;
   const int* flag_step;
   int flag_warps, flag_base, flag_per_step;
+  // Dynamic m-tile assignment of a flag consumer (weight-resident kernels): dyn_ctr[n_tile] is a monotonically growing
+  // counter; launch number e = step * flag_per_step + flag_base hands out values e * (m_tiles + CTAs per n-tile) + i,
+  // i < m_tiles being m-tile i and every CTA's last grab landing beyond.  CTAs that start late simply get fewer tiles.
+  int* dyn_ctr;
   double algo_flops;     // algorithmic FLOPs of this launch (valid frames, true N and K); profiling only
 };
 

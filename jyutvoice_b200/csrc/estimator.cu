@@ -228,6 +228,7 @@ struct FwdCtx {
   cudaStream_t st;
   // tile-level dataflow (solver only, JYUTVOICE_B200_FLAGS=1): per-m-tile counters for out-proj -> FF1 and FF2 -> next QKV
   int *flag_a = nullptr, *flag_b = nullptr;
+  int *dyn_a = nullptr, *dyn_b = nullptr;  // dynamic tile counters of the two consumers (8 n-tiles each at most)
   mutable int n_a = 0, n_b = 0;       // launches so far in this forward that bump flag_a / flag_b
   mutable bool qkv_by_flag = false;   // the previous launch was an FF2 that publishes flag_b for this QKV
 };
@@ -336,6 +337,7 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g.out_act = c.b.QKV; g.ldo2 = 1536;
   if (flags && c.qkv_by_flag) {  // LNX tile by tile from the previous block's FF2
     g.flag_in = c.flag_b; g.flag_step = c.b.row_tidx; g.flag_warps = 8; g.flag_base = c.n_b - 1; g.flag_per_step = N_FLAG_B;
+    g.dyn_ctr = c.dyn_b;
   }
   c.qkv_by_flag = false;
   e.gemm(g, c.st);
@@ -359,6 +361,7 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g.out_act = c.b.FF; g.ldo2 = 1024;
   if (flags) {  // LNX tile by tile from the out-proj launch just issued
     g.flag_in = c.flag_a; g.flag_step = c.b.row_tidx; g.flag_warps = 8; g.flag_base = c.n_a; g.flag_per_step = N_FLAG_A;
+    g.dyn_ctr = c.dyn_a;
     ++c.n_a;
   }
   e.gemm(g, c.st);
@@ -487,6 +490,16 @@ static bool use_flags() {
   return v == 1;
 }
 
+// JYUTVOICE_B200_DYN=0: with flags on, the consumers keep their static tile assignment
+static bool use_dyn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_DYN");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // JYUTVOICE_B200_SPLIT=1 (opt-in): a large solve runs as two concurrent half-batches.  Measured on B200 (batch 64 x 300,
 // same box, alternating runs): 2396 / 2400 audio-s/s unsplit against 2306 / 2311 split — the kernels' fixed costs
 // (prologue, resident weight loads, pipeline fill) double while the tail overlap recovers less than that.
@@ -537,7 +550,7 @@ static void carve_part(SolvePart& pt, jv_estimator* h, Arena& ar, const int32_t*
   pt.c.b = carve(ar, h->eng, L.M_alloc, R, 64);
   pt.lens_dev = ar.alloc<int>(R);
   pt.dts_dev = ar.alloc<float>(64);
-  pt.flags = ar.alloc<int>(2 * (size_t)(L.M_alloc / 128));
+  pt.flags = ar.alloc<int>(2 * (size_t)(L.M_alloc / 128) + 16);
   pt.c.M = L.M; pt.c.M_alloc = L.M_alloc; pt.c.R = R; pt.c.Tmax_len = tl;
   pt.c.valid_frames = 0;
   for (int r = 0; r < R; ++r) pt.c.valid_frames += L.row_len[r];
@@ -722,9 +735,13 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
     pt.c.temb_step = pt.c.b.temb;
     if (use_flags() && h->eng.is_bf16() && !profile_state().on) {
       const int mt = pt.c.M_alloc / 128;
-      JV_CUDA(cudaMemsetAsync(pt.flags, 0, 2 * (size_t)mt * sizeof(int), user_st));
+      JV_CUDA(cudaMemsetAsync(pt.flags, 0, (2 * (size_t)mt + 16) * sizeof(int), user_st));
       pt.c.flag_a = pt.flags;
       pt.c.flag_b = pt.flags + mt;
+      if (use_dyn()) {
+        pt.c.dyn_a = pt.flags + 2 * mt;
+        pt.c.dyn_b = pt.flags + 2 * mt + 8;
+      }
     }
     std::vector<int> tidx(pt.c.R, 0);
     JV_CUDA(cudaMemcpyAsync(pt.lens_dev, lens_host + pt.b0, pt.B * sizeof(int), cudaMemcpyHostToDevice, user_st));

@@ -121,13 +121,17 @@ __device__ __forceinline__ void flag_release_add(int* p) {
   __threadfence();
   asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
 }
-__device__ __forceinline__ void flag_acquire_wait(const int* p, int target, int tag) {
-  int v;
+__device__ unsigned long long g_flag_stats[2];  // [0] tile waits, [1] of which had to poll more than once (debug: jv_flag_stats)
+// Returns true once the producer's LAST tile is published as well: from then on the caller skips the per-tile polls.
+__device__ __forceinline__ bool flag_acquire_wait(const int* p, const int* p_last, int target, int tag) {
+  int v, vl;
   long long t0 = 0;
   uint32_t polls = 0;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(vl) : "l"(p_last) : "memory");  // in flight next to the tile's own flag
   for (;;) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     if (v >= target) break;
+
     if ((++polls & 1023u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -137,8 +141,8 @@ __device__ __forceinline__ void flag_acquire_wait(const int* p, int target, int 
       }
     }
   }
-  __threadfence();
   asm volatile("fence.proxy.async;" ::: "memory");  // the TMA loads that follow read what the producer's TMA stores wrote
+  return vl >= target;
 }
 
 // Programmatic dependent launch: the prologue (barrier init, TMEM allocation, smem vector cache) runs while the
@@ -389,6 +393,11 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const uint32_t epi_bar = tempty_bar + 8 * MAX_ACC;     // EPI_WARPS_MAX x 16 B (residual-load barrier per warp)
   const uint32_t tmem_slot = epi_bar + 16 * EPI_WARPS_MAX;   // 4 B
   const uint32_t wres_bar = tmem_slot + 8;               // 8 B: resident weight tile landed
+  // dynamic tile queue (GemmDesc::dyn_ctr, weight-resident kernels: the LayerNorm exchange area is unused there):
+  // the TMA warp publishes the m-tile ids it grabbed, the MMA thread and the epilogue warps follow the same sequence
+  const uint32_t tileq = bars + 544, tileq_bar = bars + 576;  // 8 ints | 8 mbarriers; ring of 8 > tiles in flight (<= 5)
+  volatile int* tileq_ptr = reinterpret_cast<volatile int*>(smem_raw + (tileq - raw));
+  const bool dyn = g.dyn_ctr != nullptr;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -419,6 +428,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     }
     for (int i = 0; i < 2 * EPI_WARPS_MAX; ++i) mbar_init(epi_bar + 8 * i, 1);
     mbar_init(wres_bar, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(tileq_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -470,7 +480,21 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   // (it keeps "kernel n+2 waits for n+1, which waited for n" intact) and only the TMA producer waits, per m-tile.
   if (!g.flag_in) pdl_wait();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int flag_target = g.flag_in ? g.flag_warps * (g.flag_step[0] * g.flag_per_step + g.flag_base + 1) : 0;
+  const int flag_epoch = g.flag_in ? g.flag_step[0] * g.flag_per_step + g.flag_base : 0;
+  const int flag_target = g.flag_warps * (flag_epoch + 1);
+  const int* flag_last = g.flag_in ? g.flag_in + (g.M - 1) / BLOCK_M : nullptr;
+  if (g.flag_in && threadIdx.x == 0) {  // debug statistic: did this CTA start before the producer grid had published everything?
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag_last) : "memory");
+    atomicAdd(&g_flag_stats[0], 1ull);
+    if (v < flag_target) atomicAdd(&g_flag_stats[1], 1ull);
+  }
+  auto tile_from_queue = [&](uint32_t& seq) {  // consumers of the dynamic tile queue
+    mbar_wait(tileq_bar + 8 * (seq & 7), (seq >> 3) & 1, 8);
+    const int t = tileq_ptr[seq & 7];
+    ++seq;
+    return t;
+  };
 
   // Register re-partitioning (general kernels, 384 threads x 168 registers): the producer / MMA / allocator warpgroup
   // drops to 80 registers, the two epilogue warpgroups grow to 208 (128 x 80 + 256 x 208 <= 384 x 168; a larger request
@@ -485,10 +509,24 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const uint32_t tx_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
       const bool slab = p.slab != 0;
       const int b_rows = p.block_n / csz;  // weight rows this CTA fetches (and multicasts)
-      for (int unit = unit0; unit < p.num_units; unit += unit_step) {
+      uint32_t qseq = 0;
+      int* const ctr = dyn ? g.dyn_ctr + blockIdx.x % p.n_tiles_n : nullptr;
+      const int dyn_base = flag_epoch * (p.num_units + (int)gridDim.x / p.n_tiles_n);
+      auto publish = [&](int v) {  // counter value -> m-tile (or -1: none left), handed to the MMA thread and the epilogue warps
+        const int t = v - dyn_base < p.num_units ? v - dyn_base : -1;
+        tileq_ptr[qseq & 7] = t;
+        mbar_arrive(tileq_bar + 8 * (qseq & 7));
+        ++qseq;
+        return t;
+      };
+      bool need_flags = g.flag_in != nullptr;
+      int v_next = 0;
+      for (int unit = dyn ? publish(atomicAdd(ctr, 1)) : unit0; dyn ? unit >= 0 : unit < p.num_units;
+           unit = dyn ? publish(v_next) : unit + unit_step) {
         const int m0 = tile_m0(unit);
         const int n0 = tile_n0(unit);
-        if (g.flag_in) flag_acquire_wait(g.flag_in + m0 / BLOCK_M, flag_target, 7);
+        if (dyn) v_next = atomicAdd(ctr, 1);  // the next tile's grab is in flight while this tile's loads are issued
+        if (need_flags && flag_acquire_wait(g.flag_in + m0 / BLOCK_M, flag_last, flag_target, 7)) need_flags = false;
         if (slab) {  // one slab per 64-channel block, shared by all taps
           for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
@@ -527,7 +565,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       int acc_stage = 0;
       uint32_t acc_phase = 0;
       if (wres && unit0 < p.num_units) mbar_wait(wres_bar, 0, 6);
-      for (int unit = unit0; unit < p.num_units; unit += unit_step) {
+      uint32_t mseq = 0;
+      for (int unit = dyn ? tile_from_queue(mseq) : unit0; dyn ? unit >= 0 : unit < p.num_units;
+           unit = dyn ? tile_from_queue(mseq) : unit + unit_step) {
         mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_stage * p.acc_cols;
@@ -616,7 +656,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     int flag_pending = -1;  // m-tile whose stores were issued by this warp but not yet published through flag_out
     const int n_chunks = p.block_n >> 5;
     const float* smf = reinterpret_cast<const float*>(smem_raw + (base - raw));
-    for (int unit = unit0; unit < p.num_units; unit += unit_step, ++t_local) {
+    uint32_t eseq = 0;
+    for (int unit = dyn ? tile_from_queue(eseq) : unit0; dyn ? unit >= 0 : unit < p.num_units;
+         unit = dyn ? tile_from_queue(eseq) : unit + unit_step, ++t_local) {
       if (tile_par && (t_local % N_SUB) != sub_id) {  // another share's tile: just keep the stage / phase counters in step
         if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
         continue;
