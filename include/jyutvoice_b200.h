@@ -49,9 +49,6 @@ uint64_t jv_launch_count(void);
  * jv_launch_count).  Step 0 of a solve runs eagerly, step 1 is captured, steps 1 .. n-1 replay it; JYUTVOICE_B200_GRAPH=0
  * or a failed capture falls back to eager launches. */
 uint64_t jv_graph_launch_count(void);
-/* Debug counters of the opt-in tile-flag dataflow (JYUTVOICE_B200_FLAGS=1): consumer tile waits so far, and how many of
- * them found their producer tile not yet published (i.e. the consumer really ran ahead of the producer grid's end). */
-int jv_flag_stats(uint64_t* waits, uint64_t* waits_that_polled);
 
 /* ------------------------------------------------------------------------------------------
  * Estimator = CausalConditionalDecoder (jyutvoice/flow/decoder.py:798-1018) with the

@@ -29,7 +29,6 @@ SIGNATURES = {
     "jv_last_error": (ctypes.c_char_p, []),
     "jv_launch_count": (ctypes.c_uint64, []),
     "jv_graph_launch_count": (ctypes.c_uint64, []),
-    "jv_flag_stats": (c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "jv_estimator_create": (c_int, [c_int, c_int, ctypes.POINTER(c_void_p)]),
     "jv_estimator_destroy": (None, [c_void_p]),
     "jv_estimator_set_weight": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, P_i64, c_int]),

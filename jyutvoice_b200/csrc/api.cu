@@ -21,14 +21,6 @@ int jv_version(void) { return 1; }
 const char* jv_last_error(void) { return g_last_error.c_str(); }
 uint64_t jv_launch_count(void) { return g_launch_count.load(); }
 uint64_t jv_graph_launch_count(void) { return g_graph_launches.load(); }
-int jv_flag_stats(uint64_t* waits, uint64_t* waits_that_polled) {
-  JV_API_BEGIN
-  unsigned long long h[2] = {0, 0};
-  JV_CUDA(cudaMemcpyFromSymbol(h, jv::tc::g_flag_stats, sizeof(h)));
-  if (waits) *waits = h[0];
-  if (waits_that_polled) *waits_that_polled = h[1];
-  JV_API_END
-}
 
 int jv_profile_begin(void) {
   JV_API_BEGIN

@@ -224,18 +224,6 @@ struct GemmDesc {
   long o_rows;           // out_row must be < o_rows
   int x_bf16;            // tcgen05 engine only: `resid` and `out_f32` point to 16-bit tensors (16-bit residual stream) ...
   int x_in_half, x_out_half;  // ... holding fp16 (11-bit significand, stores saturate) instead of bf16
-  // Tile-level dataflow between two row-local GEMMs of a solve (tcgen05 engine, N <= 256 producer): the producer bumps
-  // flag_out[m_tile] once per epilogue warp when that tile's stores have completed; the consumer, launched early through
-  // PDL, waits per m-tile for flag_in[m_tile] >= flag_warps * (step * flag_per_step + flag_base + 1) instead of waiting for
-  // the whole producer grid.  `flag_step` points at the device-side Euler step index.
-  int* flag_out;
-  const int* flag_in;
-  const int* flag_step;
-  int flag_warps, flag_base, flag_per_step;
-  // Dynamic m-tile assignment of a flag consumer (weight-resident kernels): dyn_ctr[n_tile] is a monotonically growing
-  // counter; launch number e = step * flag_per_step + flag_base hands out values e * (m_tiles + CTAs per n-tile) + i,
-  // i < m_tiles being m-tile i and every CTA's last grab landing beyond.  CTAs that start late simply get fewer tiles.
-  int* dyn_ctr;
   double algo_flops;     // algorithmic FLOPs of this launch (valid frames, true N and K); profiling only
 };
 

@@ -226,11 +226,6 @@ struct FwdCtx {
   long valid_frames;            // sum of row lengths (algorithmic FLOP accounting)
   const float* temb_step;       // temb rows of the current step: [*, 14, 256]
   cudaStream_t st;
-  // tile-level dataflow (solver only, JYUTVOICE_B200_FLAGS=1): per-m-tile counters for out-proj -> FF1 and FF2 -> next QKV
-  int *flag_a = nullptr, *flag_b = nullptr;
-  int *dyn_a = nullptr, *dyn_b = nullptr;  // dynamic tile counters of the two consumers (8 n-tiles each at most)
-  mutable int n_a = 0, n_b = 0;       // launches so far in this forward that bump flag_a / flag_b
-  mutable bool qkv_by_flag = false;   // the previous launch was an FF2 that publishes flag_b for this QKV
 };
 
 static GemmDesc conv_desc(const FwdCtx& c, const PackedW& w, const void* A0p, const void* A1p, int Kw) {
@@ -324,30 +319,20 @@ static bool use_mlp_fused() {
   return v == 1;
 }
 
-// launches per estimator forward that publish flag_a (every out-proj) / flag_b (every FF2 followed by a QKV of the same group)
-constexpr int N_FLAG_A = N_RESNET * N_TB, N_FLAG_B = N_RESNET * (N_TB - 1);
-
 // BasicTransformerBlock (transformer.py:355-443).  On entry LNX = norm1(X).  `next_ln`: norm1 of the following
 // block (fused into the FF2 epilogue) or null; `copy_to`: activation-typed copy of the block output (conv input).
 static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, void* copy_to) {
   Engine& e = c.h->eng;
-  const bool xb = e.is_bf16();
-  const bool flags = xb && c.flag_a != nullptr;
   GemmDesc g = conv_desc(c, w.qkv, c.b.LNX, nullptr, 1);
   g.out_act = c.b.QKV; g.ldo2 = 1536;
-  if (flags && c.qkv_by_flag) {  // LNX tile by tile from the previous block's FF2
-    g.flag_in = c.flag_b; g.flag_step = c.b.row_tidx; g.flag_warps = 8; g.flag_base = c.n_b - 1; g.flag_per_step = N_FLAG_B;
-    g.dyn_ctr = c.dyn_b;
-  }
-  c.qkv_by_flag = false;
   e.gemm(g, c.st);
   run_attention(c);
+  const bool xb = e.is_bf16();
   g = conv_desc(c, w.out, c.b.ATT, nullptr, 1);  // x += to_out(attn) ; LNX = norm3(x)
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
   g.x_bf16 = g.x_in_half = g.x_out_half = xb;
   set_ln2(c, g, w.n3);
-  if (flags) g.flag_out = c.flag_a;
   e.gemm(g, c.st);
   if (xb && use_mlp_fused()) {  // FF1 + GELU + FF2 + residual (+ next norm1) in one kernel: the hidden never leaves the SM
     const bool to_copy = copy_to != nullptr;
@@ -359,11 +344,6 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g = conv_desc(c, w.ff1, c.b.LNX, nullptr, 1);
   g.act = ACT_GELU;
   g.out_act = c.b.FF; g.ldo2 = 1024;
-  if (flags) {  // LNX tile by tile from the out-proj launch just issued
-    g.flag_in = c.flag_a; g.flag_step = c.b.row_tidx; g.flag_warps = 8; g.flag_base = c.n_a; g.flag_per_step = N_FLAG_A;
-    g.dyn_ctr = c.dyn_a;
-    ++c.n_a;
-  }
   e.gemm(g, c.st);
   g = conv_desc(c, w.ff2, c.b.FF, nullptr, 1);  // x += ff(norm3(x)) ; LNX = next norm1(x)
   g.resid = c.b.X; g.ldr = C;
@@ -373,11 +353,6 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   if (copy_to) {
     if (xb) { g.out_f32 = (float*)copy_to; g.x_out_half = 0; }  // bf16 copy for the next conv; X is not read again in this group
     else { g.out_act = copy_to; g.ldo2 = C; }
-  }
-  if (flags && next_ln) {  // the next launch is the following block's QKV
-    g.flag_out = c.flag_b;
-    ++c.n_b;
-    c.qkv_by_flag = true;
   }
   e.gemm(g, c.st);
 }
@@ -398,8 +373,6 @@ static void forward_packed(const FwdCtx& c) {
   Engine& e = h->eng;
   e.scratch = c.b.Y;
   e.scratch_rows = c.M_alloc;
-  c.n_a = c.n_b = 0;
-  c.qkv_by_flag = false;
   for (int gi = 0; gi < N_RESNET; ++gi) {
     const GroupW& G = h->groups[gi];
     const void* in0 = gi == 0 ? c.b.A0 : (gi == 1 ? c.b.XB : c.b.XA);  // XB: output of the down CausalConv1d
@@ -480,26 +453,6 @@ static void run_pack(const FwdCtx& c, const float* x, const float* mu, const flo
   else launch_pack<float>(c, x, mu, spks, cond, Tmax, cfg);
 }
 
-// JYUTVOICE_B200_FLAGS=1 (opt-in): tile-level dataflow between out-proj -> FF1 and FF2 -> QKV inside a solve (GemmDesc::flag_*)
-static bool use_flags() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("JYUTVOICE_B200_FLAGS");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-// JYUTVOICE_B200_DYN=0: with flags on, the consumers keep their static tile assignment
-static bool use_dyn() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("JYUTVOICE_B200_DYN");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
 // JYUTVOICE_B200_SPLIT=1 (opt-in): a large solve runs as two concurrent half-batches.  Measured on B200 (batch 64 x 300,
 // same box, alternating runs): 2396 / 2400 audio-s/s unsplit against 2306 / 2311 split — the kernels' fixed costs
 // (prologue, resident weight loads, pipeline fill) double while the tail overlap recovers less than that.
@@ -534,7 +487,6 @@ struct SolvePart {
   FwdCtx c;
   int* lens_dev = nullptr;
   float* dts_dev = nullptr;
-  int* flags = nullptr;  // 2 x m_tiles counters (FwdCtx::flag_a / flag_b)
 };
 
 static void carve_part(SolvePart& pt, jv_estimator* h, Arena& ar, const int32_t* lens_host, int* tmax_len, EstLayout* Lout) {
@@ -550,7 +502,6 @@ static void carve_part(SolvePart& pt, jv_estimator* h, Arena& ar, const int32_t*
   pt.c.b = carve(ar, h->eng, L.M_alloc, R, 64);
   pt.lens_dev = ar.alloc<int>(R);
   pt.dts_dev = ar.alloc<float>(64);
-  pt.flags = ar.alloc<int>(2 * (size_t)(L.M_alloc / 128) + 16);
   pt.c.M = L.M; pt.c.M_alloc = L.M_alloc; pt.c.R = R; pt.c.Tmax_len = tl;
   pt.c.valid_frames = 0;
   for (int r = 0; r < R; ++r) pt.c.valid_frames += L.row_len[r];
@@ -733,16 +684,6 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
     carve_part(pt, h, ar, lens_host, nullptr, &L);
     pt.c.st = user_st;
     pt.c.temb_step = pt.c.b.temb;
-    if (use_flags() && h->eng.is_bf16() && !profile_state().on) {
-      const int mt = pt.c.M_alloc / 128;
-      JV_CUDA(cudaMemsetAsync(pt.flags, 0, (2 * (size_t)mt + 16) * sizeof(int), user_st));
-      pt.c.flag_a = pt.flags;
-      pt.c.flag_b = pt.flags + mt;
-      if (use_dyn()) {
-        pt.c.dyn_a = pt.flags + 2 * mt;
-        pt.c.dyn_b = pt.flags + 2 * mt + 8;
-      }
-    }
     std::vector<int> tidx(pt.c.R, 0);
     JV_CUDA(cudaMemcpyAsync(pt.lens_dev, lens_host + pt.b0, pt.B * sizeof(int), cudaMemcpyHostToDevice, user_st));
     JV_CUDA(cudaMemcpyAsync(pt.dts_dev, dts.data(), n_timesteps * sizeof(float), cudaMemcpyHostToDevice, user_st));

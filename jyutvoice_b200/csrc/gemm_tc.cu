@@ -329,14 +329,12 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 2 : 1;
-  GemmDesc gl = g;
-  if (gl.dyn_ctr && (!p.wres || p.tile_par || p.n_tiles_n > 8)) gl.dyn_ctr = nullptr;  // static assignment otherwise
   KernelFn fn = kernel_table()[N_KERNELS - 1].fn;  // generic
   bool found = false;
   for (int i = 0; i < N_KERNELS - 1; ++i)
     if (kernel_table()[i].epi == epi) { fn = kernel_table()[i].fn; found = true; }
   JV_REQUIRE(found || !g.x_bf16, JV_ERR_INVALID, "no bf16-stream kernel for epilogue kind %d", epi);
-  JV_CUDA(cudaLaunchKernelEx(&cfg, fn, tm, gl, p));
+  JV_CUDA(cudaLaunchKernelEx(&cfg, fn, tm, g, p));
   JV_LAUNCHED();
   if (ps.on) {
     JV_CUDA(cudaEventRecord(e1, st));

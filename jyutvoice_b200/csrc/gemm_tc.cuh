@@ -116,35 +116,6 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// tile flags (GemmDesc::flag_*): release increment after a tile's stores completed / acquire poll before a tile's loads
-__device__ __forceinline__ void flag_release_add(int* p) {
-  __threadfence();
-  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
-}
-__device__ unsigned long long g_flag_stats[2];  // [0] tile waits, [1] of which had to poll more than once (debug: jv_flag_stats)
-// Returns true once the producer's LAST tile is published as well: from then on the caller skips the per-tile polls.
-__device__ __forceinline__ bool flag_acquire_wait(const int* p, const int* p_last, int target, int tag) {
-  int v, vl;
-  long long t0 = 0;
-  uint32_t polls = 0;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(vl) : "l"(p_last) : "memory");  // in flight next to the tile's own flag
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    if (v >= target) break;
-
-    if ((++polls & 1023u) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 4000000000LL) {
-        printf("jyutvoice_b200: tile flag wait timed out (tag %d, block %d, have %d, want %d)\n", tag, blockIdx.x, v, target);
-        __trap();
-      }
-    }
-  }
-  asm volatile("fence.proxy.async;" ::: "memory");  // the TMA loads that follow read what the producer's TMA stores wrote
-  return vl >= target;
-}
-
 // Programmatic dependent launch: the prologue (barrier init, TMEM allocation, smem vector cache) runs while the
 // previous kernel in the stream drains; nothing produced by that kernel is touched before pdl_wait().
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -393,11 +364,6 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const uint32_t epi_bar = tempty_bar + 8 * MAX_ACC;     // EPI_WARPS_MAX x 16 B (residual-load barrier per warp)
   const uint32_t tmem_slot = epi_bar + 16 * EPI_WARPS_MAX;   // 4 B
   const uint32_t wres_bar = tmem_slot + 8;               // 8 B: resident weight tile landed
-  // dynamic tile queue (GemmDesc::dyn_ctr, weight-resident kernels: the LayerNorm exchange area is unused there):
-  // the TMA warp publishes the m-tile ids it grabbed, the MMA thread and the epilogue warps follow the same sequence
-  const uint32_t tileq = bars + 544, tileq_bar = bars + 576;  // 8 ints | 8 mbarriers; ring of 8 > tiles in flight (<= 5)
-  volatile int* tileq_ptr = reinterpret_cast<volatile int*>(smem_raw + (tileq - raw));
-  const bool dyn = g.dyn_ctr != nullptr;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -428,7 +394,6 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     }
     for (int i = 0; i < 2 * EPI_WARPS_MAX; ++i) mbar_init(epi_bar + 8 * i, 1);
     mbar_init(wres_bar, 1);
-    for (int i = 0; i < 8; ++i) mbar_init(tileq_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -475,26 +440,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     for (int it = 0; it < k_iters; ++it)
       tma_load_2d(&tm.w, wres_bar, smem_b + it * p.b_stage_bytes, it * BLOCK_K, tile_n0(unit0));
   }
-  // from here on the previous kernel's results (activations, residual stream) may be read / overwritten — unless this
-  // launch consumes its A operand tile by tile through flags: then the grid-wide wait moves to the end of the kernel
-  // (it keeps "kernel n+2 waits for n+1, which waited for n" intact) and only the TMA producer waits, per m-tile.
-  if (!g.flag_in) pdl_wait();
+  pdl_wait();  // from here on the previous kernel's results (activations, residual stream) may be read / overwritten
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int flag_epoch = g.flag_in ? g.flag_step[0] * g.flag_per_step + g.flag_base : 0;
-  const int flag_target = g.flag_warps * (flag_epoch + 1);
-  const int* flag_last = g.flag_in ? g.flag_in + (g.M - 1) / BLOCK_M : nullptr;
-  if (g.flag_in && threadIdx.x == 0) {  // debug statistic: did this CTA start before the producer grid had published everything?
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag_last) : "memory");
-    atomicAdd(&g_flag_stats[0], 1ull);
-    if (v < flag_target) atomicAdd(&g_flag_stats[1], 1ull);
-  }
-  auto tile_from_queue = [&](uint32_t& seq) {  // consumers of the dynamic tile queue
-    mbar_wait(tileq_bar + 8 * (seq & 7), (seq >> 3) & 1, 8);
-    const int t = tileq_ptr[seq & 7];
-    ++seq;
-    return t;
-  };
 
   // Register re-partitioning (general kernels, 384 threads x 168 registers): the producer / MMA / allocator warpgroup
   // drops to 80 registers, the two epilogue warpgroups grow to 208 (128 x 80 + 256 x 208 <= 384 x 168; a larger request
@@ -509,24 +456,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const uint32_t tx_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
       const bool slab = p.slab != 0;
       const int b_rows = p.block_n / csz;  // weight rows this CTA fetches (and multicasts)
-      uint32_t qseq = 0;
-      int* const ctr = dyn ? g.dyn_ctr + blockIdx.x % p.n_tiles_n : nullptr;
-      const int dyn_base = flag_epoch * (p.num_units + (int)gridDim.x / p.n_tiles_n);
-      auto publish = [&](int v) {  // counter value -> m-tile (or -1: none left), handed to the MMA thread and the epilogue warps
-        const int t = v - dyn_base < p.num_units ? v - dyn_base : -1;
-        tileq_ptr[qseq & 7] = t;
-        mbar_arrive(tileq_bar + 8 * (qseq & 7));
-        ++qseq;
-        return t;
-      };
-      bool need_flags = g.flag_in != nullptr;
-      int v_next = 0;
-      for (int unit = dyn ? publish(atomicAdd(ctr, 1)) : unit0; dyn ? unit >= 0 : unit < p.num_units;
-           unit = dyn ? publish(v_next) : unit + unit_step) {
+      for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         const int m0 = tile_m0(unit);
         const int n0 = tile_n0(unit);
-        if (dyn) v_next = atomicAdd(ctr, 1);  // the next tile's grab is in flight while this tile's loads are issued
-        if (need_flags && flag_acquire_wait(g.flag_in + m0 / BLOCK_M, flag_last, flag_target, 7)) need_flags = false;
         if (slab) {  // one slab per 64-channel block, shared by all taps
           for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
@@ -565,9 +497,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       int acc_stage = 0;
       uint32_t acc_phase = 0;
       if (wres && unit0 < p.num_units) mbar_wait(wres_bar, 0, 6);
-      uint32_t mseq = 0;
-      for (int unit = dyn ? tile_from_queue(mseq) : unit0; dyn ? unit >= 0 : unit < p.num_units;
-           unit = dyn ? tile_from_queue(mseq) : unit + unit_step) {
+      for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_stage * p.acc_cols;
@@ -653,12 +583,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     const int c_first = tile_par ? 0 : sub_id, c_step = tile_par ? 1 : N_SUB;
     int t_local = 0;   // tiles seen by this CTA
     uint32_t n_out = 0;  // output chunks staged by this warp (alternates the bf16 staging buffers)
-    int flag_pending = -1;  // m-tile whose stores were issued by this warp but not yet published through flag_out
     const int n_chunks = p.block_n >> 5;
     const float* smf = reinterpret_cast<const float*>(smem_raw + (base - raw));
-    uint32_t eseq = 0;
-    for (int unit = dyn ? tile_from_queue(eseq) : unit0; dyn ? unit >= 0 : unit < p.num_units;
-         unit = dyn ? tile_from_queue(eseq) : unit + unit_step, ++t_local) {
+    for (int unit = unit0; unit < p.num_units; unit += unit_step, ++t_local) {
       if (tile_par && (t_local % N_SUB) != sub_id) {  // another share's tile: just keep the stage / phase counters in step
         if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
         continue;
@@ -674,13 +601,6 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const float* v_b2 = p.vec_ln2 ? smf + p.vec_ln2 / 4 + p.block_n - n0 : g.ln2_beta;
       const float* v_act = g.act_vec ? (p.vec_act ? smf + p.vec_act / 4 - n0 : g.act_vec) : nullptr;
       const float* v_act2 = g.act2_vec ? (p.vec_act2 ? smf + p.vec_act2 / 4 - n0 : g.act2_vec) : nullptr;
-      if (g.flag_out && flag_pending >= 0) {  // the previous tile's stores have had a whole mainloop to land
-        if (lane == 0) {
-          bulk_wait0();
-          flag_release_add(g.flag_out + flag_pending);
-        }
-        flag_pending = -1;
-      }
       if (XB) {  // residual of the first two chunks: in flight while the accumulator is still being computed
         if (lane == 0) {
           mbar_expect_tx(ebar, EPI_B16_BYTES);
@@ -876,14 +796,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       tc_fence_before();
       mbar_arrive(tempty_bar + 8 * grp);
       if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
-      if (g.flag_out) flag_pending = m0 / BLOCK_M;
     }
-    if (lane == 0) {
-      bulk_wait0();  // smem must outlive the last TMA store's reads
-      if (g.flag_out && flag_pending >= 0) flag_release_add(g.flag_out + flag_pending);
-    }
+    if (lane == 0) bulk_wait0();  // smem must outlive the last TMA store's reads
   }
-  if (g.flag_in) pdl_wait();  // see above: every thread, after its role's work
 
   tc_fence_before();
   __syncthreads();
