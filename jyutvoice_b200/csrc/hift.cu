@@ -225,7 +225,8 @@ struct HiftBuffers {
   float* SPEC;                   // [rows2, 32]
 };
 
-static HiftBuffers hift_carve(Arena& ar, const Engine& eng, const HiftLayout& L, int Tmax) {
+// `Tlong` = longest utterance of the batch (NOT the caller's tensor stride: jv_hift_workspace_bytes sees only the lengths)
+static HiftBuffers hift_carve(Arena& ar, const Engine& eng, const HiftLayout& L, int Tlong) {
   HiftBuffers b;
   const size_t es = eng.act_size();
   b.off = ar.alloc<int>(L.B + 1);
@@ -234,7 +235,7 @@ static HiftBuffers hift_carve(Arena& ar, const Engine& eng, const HiftLayout& L,
   b.MEL = ar.alloc<char>((size_t)L.rows_alloc[0] * 128 * es);
   b.H1 = ar.alloc<char>((size_t)L.rows_alloc[0] * 512 * es);
   b.H2 = ar.alloc<char>((size_t)L.rows_alloc[0] * 512 * es);
-  b.D = ar.alloc<double>((size_t)L.B * 9 * Tmax);
+  b.D = ar.alloc<double>((size_t)L.B * 9 * Tlong);
   b.SST = ar.alloc<char>((size_t)L.rows_alloc[3] * 18 * es);
   {
     size_t im = 0;
@@ -260,7 +261,8 @@ struct HCtx {
   HiftLayout L;
   HiftBuffers b;
   HiftSeq sq;
-  int Tmax;
+  int Tmax;   // row stride of the caller's [B, *, Tmax] tensors
+  int Tlong;  // longest utterance: row stride of the phase-prefix scratch D
   long valid_rows[4];  // valid frames per level (algorithmic FLOP accounting)
   cudaStream_t st;
 };
@@ -274,7 +276,9 @@ static void hift_setup(HCtx& c, jv_hift* h, int B, int Tmax, const int32_t* lens
   c.h = h;
   c.L = hift_layout(B, lens);
   Arena ar(ws, ws_bytes);
-  c.b = hift_carve(ar, h->eng, c.L, Tmax);
+  c.Tlong = 0;
+  for (int b = 0; b < B; ++b) c.Tlong = std::max(c.Tlong, lens[b]);
+  c.b = hift_carve(ar, h->eng, c.L, c.Tlong);
   c.Tmax = Tmax;
   c.st = (cudaStream_t)stream;
   JV_CUDA(cudaMemcpyAsync(c.b.off, c.L.off.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, c.st));
@@ -594,10 +598,11 @@ int jv_hift_source(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const 
   JV_REQUIRE(f0 && phase && noise && s, JV_ERR_INVALID, "bad arguments");
   HCtx c;
   hift_setup(c, h, B, Tmax, lens_host, ws, ws_bytes, stream);
-  hift_phase_prefix_kernel<<<cdiv(B * 9, 64), 64, 0, c.st>>>(f0, Tmax, c.b.len, B, c.b.D);
+  hift_phase_prefix_kernel<<<cdiv(B * 9, 64), 64, 0, c.st>>>(f0, Tmax, c.b.len, B, c.b.D, c.Tlong);
   JV_LAUNCHED();
   const long n = (long)B * 480 * Tmax;
-  hift_source_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(f0, c.b.D, phase, noise, h->src_w, h->src_b, c.b.len, B, Tmax, s);
+  hift_source_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(f0, c.b.D, phase, noise, h->src_w, h->src_b, c.b.len, B, Tmax, s,
+                                                                    c.Tlong);
   JV_LAUNCHED();
   JV_API_END
 }

@@ -66,15 +66,17 @@ __global__ void zero_f32_kernel(float* __restrict__ p, long n) {
 // ---------------------------------------------------------------- NSF source (generator.py:141-176, 220-236)
 // Phase prefix per (b, harmonic): D[b,h,t] = sum_{t'<t} 480 * F[b,h,t'] accumulated in fp64 — torch's CPU
 // cumsum accumulates fp32 inputs in double and rounds each output to float (ATen cumsum_cpu_kernel, acc_type).
+// D has row stride Dld = the longest utterance (<= Tmax, the row stride of the caller's tensors): the workspace query
+// sees only the lengths.
 __global__ void hift_phase_prefix_kernel(const float* __restrict__ f0, int Tmax, const int* __restrict__ len, int B,
-                                         double* __restrict__ D) {
+                                         double* __restrict__ D, int Dld) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 9) return;
   int b = i / 9, h = i % 9;
   double acc = 0.0;
   const int T = len[b];
   for (int t = 0; t < T; ++t) {
-    D[((long)b * 9 + h) * Tmax + t] = acc;
+    D[((long)b * 9 + h) * Dld + t] = acc;
     float F = f0[(long)b * Tmax + t] * (float)(h + 1) / 24000.0f;
     acc += 480.0 * (double)F;
   }
@@ -82,7 +84,7 @@ __global__ void hift_phase_prefix_kernel(const float* __restrict__ f0, int Tmax,
 
 __global__ void hift_source_kernel(const float* __restrict__ f0, const double* __restrict__ D, const float* __restrict__ phase,
                                    const float* __restrict__ noise, const float* __restrict__ lw, const float* __restrict__ lb,
-                                   const int* __restrict__ len, int B, int Tmax, float* __restrict__ s) {
+                                   const int* __restrict__ len, int B, int Tmax, float* __restrict__ s, int Dld) {
   const long L = 480L * Tmax;
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * L) return;
@@ -97,7 +99,7 @@ __global__ void hift_source_kernel(const float* __restrict__ f0, const double* _
 #pragma unroll
   for (int h = 0; h < 9; ++h) {
     const float F = f * (float)(h + 1) / 24000.0f;
-    const double cum = D[((long)b * 9 + h) * Tmax + t] + (double)(jj + 1) * (double)F;
+    const double cum = D[((long)b * 9 + h) * Dld + t] + (double)(jj + 1) * (double)F;
     const float cf = (float)cum;
     const float frac = cf - floorf(cf);  // fp32 `% 1` of a non-negative value
     const float theta = 6.283185307179586f * frac;

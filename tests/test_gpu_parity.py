@@ -427,6 +427,33 @@ def test_hift_full_size_properties(hifts):
     assert snr_db(one[0], wav[5]) >= 55.0
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_padded_tensors_longer_than_every_utterance(cfms, hifts, prec, hift_sd, est_sd, noise_bank):
+    """The caller's tensors may be padded beyond the longest utterance (T = 48 > max(lens) = 41): the workspace queries
+    see only the lengths, so nothing sized by them may use the tensor stride (regression: 8-GPU bench, ranks whose random
+    lengths did not reach the padded width)."""
+    from oracle import estimator as oe, hift as oh
+    lens = [41, 30]
+    T = 48
+    g = torch.Generator().manual_seed(48)
+    mu = torch.randn(2, 80, T, generator=g)
+    spks = torch.randn(2, 80, generator=g)
+    mel, _ = cfms[prec](mu.cuda(), None, 2, 1.0, spks.cuda(), None, lengths=lens)
+    with torch.no_grad():
+        ref = oe.cfm_forward_batch(est_sd, noise_bank, mu, lens, 2, 1.0, spks, None)
+    assert (mel.cpu() - ref).abs().max().item() <= (FP32_MEL_TOL if prec == "fp32" else BF16_MEL_TOL)
+    assert float(mel[:, :, 41:].abs().max()) == 0.0
+    hift = hifts[(prec, "voiced")]
+    x = (torch.randn(2, 80, T, generator=g) * 2 - 5)
+    wav, s = hift.inference(x.cuda(), lengths=lens)
+    assert wav.shape == (2, 480 * T) and s.shape == (2, 1, 480 * T)
+    for i, l in enumerate(lens):  # each utterance equals its own unpadded call (same RNG draws are not shared: compare decode)
+        one = hift.decode(x[i:i + 1, :, :l].contiguous().cuda(), s[i:i + 1, :, : 480 * l].contiguous())
+        both = hift.decode(x.cuda(), s, lengths=lens)
+        assert snr_db(one.cpu(), both[i:i + 1, : 480 * l].cpu()) >= (FP32_SNR if prec == "fp32" else 55.0)
+        assert float(both[i, 480 * l:].abs().max()) == 0.0
+
+
 def test_inference_draws_rng_like_the_reference(hifts):
     """Default rng: Uniform on CPU, randn on the device, in the reference's order (generator.py:155-158,171,235)."""
     hift = hifts[("fp32", "unvoiced")]
