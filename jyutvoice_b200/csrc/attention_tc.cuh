@@ -306,11 +306,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 
 static inline void launch_attention_tc(TmapCache& cache, const void* qkv, void* out, const int* row_off, const int* row_len,
                                        long M_alloc, int R, int Tmax_len, int chunk, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr))
     JV_CUDA(cudaFuncSetAttribute(attn::attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES));
-    attr = true;
-  }
   const CUtensorMap tm = cache.get(qkv, 1536, M_alloc, 1536 * 2, 64, attn::TQ, 0);
   const CUtensorMap tmkv = cache.get(qkv, 1536, M_alloc, 1536 * 2, 64, attn::TK, 0);
   dim3 grid(cdiv(Tmax_len, attn::TQ), 8, R);

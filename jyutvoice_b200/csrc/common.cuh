@@ -72,6 +72,16 @@ struct Arena {
   }
 };
 
+// cudaFuncSetAttribute is per device: true the first time `site` is asked about the CURRENT device (handles on several
+// devices may live in one process; a process-wide "done" flag would leave the second device without its smem opt-in)
+static inline bool first_use_on_device(unsigned long long& site) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (site & (1ull << dev)) return false;
+  site |= 1ull << dev;
+  return true;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return cdiv(a, b) * b; }
 

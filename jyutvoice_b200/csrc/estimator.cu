@@ -257,11 +257,9 @@ static void run_attention(const FwdCtx& c) {
     launch_attention_tc(c.h->eng.tmaps, c.b.QKV, c.b.ATT, c.b.row_off, c.b.row_len, c.M_alloc, c.R, c.Tmax_len, c.h->chunk, c.st);
     return;
   }
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr))
     JV_CUDA(cudaFuncSetAttribute(attention_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
-    attr = true;
-  }
   dim3 grid(cdiv(c.Tmax_len, 64), 8, c.R);
   attention_simt_kernel<float><<<grid, 256, ATT_SMEM_BYTES, c.st>>>((const float*)c.b.QKV, 1536, (float*)c.b.ATT, 512, c.b.row_off,
                                                                     c.b.row_len, 0.125f, c.h->chunk);

@@ -171,11 +171,10 @@ static const CUtensorMap& out_view(TmapCache& cache, const GemmDesc& g, const vo
 
 void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;
+  if (first_use_on_device(attr_set)) {
     for (int i = 0; i < N_KERNELS; ++i)
       JV_CUDA(cudaFuncSetAttribute((const void*)kernel_table()[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
-    attr_set = true;
   }
   tc::TcParams p;
   p.block_n = g.N <= 256 ? round_up(g.N, 32) : wide_block_n(g.N);

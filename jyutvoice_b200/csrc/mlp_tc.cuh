@@ -359,11 +359,9 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
                                     const float* b2, const void* x_in, void* out, int out_half, const float* gamma,
                                     const float* beta, void* lnx_out, const int* frame_row, long M_alloc, int num_sms,
                                     double algo_flops, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr))
     JV_CUDA(cudaFuncSetAttribute(mlp::mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-    attr = true;
-  }
   JV_REQUIRE(mlp::SMEM_BYTES <= tc::SMEM_LIMIT, JV_ERR_STATE, "fused MLP: shared memory budget exceeded");
   mlp::Maps tm;
   tm.a = cache.get(lnx_in, 256, M_alloc, 256 * 2, 64, 128, 0);
