@@ -93,6 +93,50 @@ def synth_golden():
         print(name, "T =", int(out["mel_lengths"][0]))
 
 
+def module_inputs(seed):
+    """Inputs of the per-module fixtures: a ragged 3-row batch of 45 frames."""
+    g = torch.Generator().manual_seed(seed)
+    lens = [45, 17, 32]
+    T = 45
+    mask = torch.zeros(3, 1, T)
+    for i, l in enumerate(lens):
+        mask[i, 0, :l] = 1
+    x320 = torch.randn(3, 320, T, generator=g)
+    x256 = torch.randn(3, 256, T, generator=g)
+    temb = torch.randn(3, 1024, generator=g)
+    xh = torch.randn(2, 64, 333, generator=g)  # HiFT stage-2 shaped ResBlock input
+    return lens, mask, x320, x256, temb, xh
+
+
+def module_golden():
+    """Per-module outputs of the UNMODIFIED reference submodules: CausalBlock1D, CausalResnetBlock1D, BasicTransformerBlock
+    with a ragged key mask, and two HiFT ResBlocks (kernel 3 and 11) — they pin the oracle below the estimator / decode level."""
+    ref_shims.install()
+    from jyutvoice.utils.mask import add_optional_chunk_mask
+    from jyutvoice.utils.common import mask_to_bias
+    cfm = ref_shims.build_reference_cfm()
+    cfm.load_state_dict(weights.make_estimator_state_dict(), strict=True)
+    est = cfm.estimator
+    hift = ref_shims.build_reference_hift()
+    hift.load_state_dict(weights.make_hift_state_dict(), strict=True)
+    lens, mask, x320, x256, temb, xh = module_inputs(31)
+    out = {"seed": 31}
+    with torch.no_grad():
+        resnet0 = est.down_blocks[0][0]
+        out["causal_block"] = resnet0.block1(x320, mask).numpy()            # down_blocks.0.0.block1 (320 -> 256)
+        out["resnet"] = resnet0(x320, mask, temb).numpy()                   # down_blocks.0.0
+        mid = est.mid_blocks[3][0]
+        out["resnet_mid"] = mid(x256, mask, temb).numpy()                   # mid_blocks.3.0 (256 -> 256)
+        tb = est.mid_blocks[3][1][2]                                        # mid_blocks.3.1.2
+        h = x256.transpose(1, 2).contiguous()
+        am = add_optional_chunk_mask(h, mask.bool(), False, False, 0, 0, -1).repeat(1, h.size(1), 1)
+        out["tblock"] = tb(hidden_states=h, attention_mask=mask_to_bias(am, h.dtype), timestep=None).numpy()
+        out["hift_resblock_s2_k3"] = hift.resblocks[6](xh).numpy()          # stage 2, kernel 3
+        out["hift_resblock_s2_k11"] = hift.resblocks[8](xh).numpy()         # stage 2, kernel 11
+    np.savez_compressed(os.path.join(OUT, "modules.npz"), **out)
+    print("modules", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -182,6 +226,8 @@ def main():
         cases[f"c{ci}_y_mask"] = y_mask.numpy()
     cases["n_cases"] = 5
     np.savez_compressed(os.path.join(OUT, "lengths.npz"), **cases)
+    # ---------------- per-module fixtures ----------------
+    module_golden()
     # ---------------- end to end: the reference's JyutVoiceTTS.synthesise (config 1 of BASELINE.json) ----------------
     synth_golden()
     for f in sorted(os.listdir(OUT)):

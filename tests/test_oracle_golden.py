@@ -54,6 +54,28 @@ def test_streaming_golden(est_sd, noise_bank):
     assert (mel - torch.from_numpy(g["out"])).abs().max().item() <= 1e-4
 
 
+def test_module_goldens(est_sd, hift_sd):
+    """Per-module fixtures from the reference's own submodules: CausalBlock1D, two ResNet blocks,
+    a transformer block with a ragged key mask, two HiFT ResBlocks."""
+    from oracle.make_golden import module_inputs
+    g = np.load(os.path.join(GOLDEN, "modules.npz"))
+    lens, mask, x320, x256, temb, xh = module_inputs(int(g["seed"]))
+    p = "estimator."
+    with torch.no_grad():
+        cb = oe.causal_block(est_sd, p + "down_blocks.0.0.block1", x320, mask)
+        rn = oe.resnet(est_sd, p + "down_blocks.0.0", x320, mask, temb)
+        rm = oe.resnet(est_sd, p + "mid_blocks.3.0", x256, mask, temb)
+        tb = oe.tblock(est_sd, p + "mid_blocks.3.1.2", x256.transpose(1, 2).contiguous(), oe.attn_bias(mask, 45))
+        r3 = oh.resblock(hift_sd, "resblocks.6", xh, 3)
+        r11 = oh.resblock(hift_sd, "resblocks.8", xh, 11)
+    for name, got in (("causal_block", cb), ("resnet", rn), ("resnet_mid", rm), ("tblock", tb), ("hift_resblock_s2_k3", r3),
+                      ("hift_resblock_s2_k11", r11)):
+        ref = torch.from_numpy(g[name])
+        assert got.shape == ref.shape, name
+        assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), name
+    assert float(cb[1, :, 17:].abs().max()) == 0.0  # CausalBlock1D re-applies the mask
+
+
 @pytest.mark.parametrize("name", ["cfm_T33_n4", "cfm_T50_n10"])
 def test_cfm_golden(est_sd, noise_bank, name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
