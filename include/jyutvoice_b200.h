@@ -18,7 +18,8 @@
  *   - a handle is bound to one device and must not be used from two threads at once.
  *   - precision: JV_PREC_FP32 computes every contraction in fp32 FFMA (the <=1e-3 / >=60 dB mode);
  *     JV_PREC_BF16 runs contractions on tcgen05 tensor cores with bf16 operands, fp32 accumulation,
- *     fp32 normalisation statistics and an fp32 residual stream.
+ *     fp32 normalisation statistics; the estimator's residual stream is stored in 16 bits between epilogues
+ *     (jv_estimator_set_stream_format), HiFT's in fp32.
  */
 #ifndef JYUTVOICE_B200_H
 #define JYUTVOICE_B200_H
@@ -49,6 +50,9 @@ uint64_t jv_launch_count(void);
  * jv_launch_count).  Step 0 of a solve runs eagerly, step 1 is captured, steps 1 .. n-1 replay it; JYUTVOICE_B200_GRAPH=0
  * or a failed capture falls back to eager launches. */
 uint64_t jv_graph_launch_count(void);
+/* bf16-mode GEMMs whose shape the tcgen05 kernel cannot run and that were lowered to the FFMA engine instead (~50x
+ * slower; reported once on stderr).  0 for the configs/base.yaml graphs. */
+uint64_t jv_simt_fallback_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Estimator = CausalConditionalDecoder (jyutvoice/flow/decoder.py:798-1018) with the
@@ -68,6 +72,18 @@ int jv_estimator_finalize(jv_estimator* h);
  * sees keys < min(len, (t / chunk_size + 1) * chunk_size).  chunk_size = static_chunk_size (50) turns it on, 0 (the
  * default) restores full context.  State of the handle: applies to every later jv_estimator_forward / jv_cfm_solve. */
 int jv_estimator_set_chunk(jv_estimator* h, int chunk_size);
+
+/* bf16 mode stores the residual stream in 16 bits between GEMM epilogues: format 0 = fp16 with saturating stores
+ * (default: 11 significand bits), 1 = bf16 (8 bits, fp32 range: for weights whose activations exceed +-65504). */
+int jv_estimator_set_stream_format(jv_estimator* h, int format);
+/* Rows of the fp16 stream whose sum of squares reached 65504^2 since finalize (a conservative test: 0 means no stored
+ * value can have saturated).  synchronize = 0 returns the value as of the last completed forward / solve (a pinned
+ * host copy refreshed on the caller's stream); synchronize != 0 waits for the device first. */
+int jv_estimator_saturation_count(jv_estimator* h, int synchronize, int64_t* count);
+/* The time conditioning of n timesteps t (decoder.py:15-30 SinusoidalPosEmb, :127-171 TimestepEmbedding, :101-103 the
+ * resnets' Mish -> Linear): out dev [n, 14, 256], resnet order down, mid 0..11, up.  Inspection / test hook (the
+ * solver computes the same table once per solve); synchronises the stream. */
+int jv_estimator_time_embedding(jv_estimator* h, const float* t_host, int n, float* out, void* stream);
 
 /* Workspace for B utterances (R = 2B estimator rows with CFG) of the given lengths. */
 size_t jv_cfm_workspace_bytes(const jv_estimator* h, int n_rows, const int32_t* lens_host);
@@ -112,6 +128,11 @@ int jv_hift_f0(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const floa
  * randn_like draw) -> s dev [B,480*Tmax].  The caller draws the RNG exactly as the reference does. */
 int jv_hift_source(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* f0,
                    const float* phase, const float* noise, float* s, void* ws, size_t ws_bytes, void* stream);
+/* HiFTGenerator._stft (generator.py:371-381): s dev [B,480*Tmax] -> out dev [B,18,120*Tmax+1] = [real(9) | imag(9)],
+ * frames beyond 120*len_b + 1 are 0 (each utterance reflect-padded at its own length).  Inspection / test hook: decode
+ * computes the same tensor internally (in bf16 mode it is rounded to bf16 there and here). */
+int jv_hift_stft(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* s, float* out,
+                 void* ws, size_t ws_bytes, void* stream);
 /* HiFTGenerator.decode(x=mel, s) (generator.py:396-432): -> wav dev [B,480*Tmax]; samples beyond
  * 480*len_b are 0.  Each utterance is decoded with its own zero boundary, i.e. equals the
  * reference's unpadded batch-1 call. */

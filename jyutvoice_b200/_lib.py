@@ -29,6 +29,11 @@ SIGNATURES = {
     "jv_last_error": (ctypes.c_char_p, []),
     "jv_launch_count": (ctypes.c_uint64, []),
     "jv_graph_launch_count": (ctypes.c_uint64, []),
+    "jv_simt_fallback_count": (ctypes.c_uint64, []),
+    "jv_estimator_set_stream_format": (c_int, [c_void_p, c_int]),
+    "jv_estimator_saturation_count": (c_int, [c_void_p, c_int, P_i64]),
+    "jv_estimator_time_embedding": (c_int, [c_void_p, P_f32, c_int, c_void_p, c_void_p]),
+    "jv_hift_stft": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "jv_estimator_create": (c_int, [c_int, c_int, ctypes.POINTER(c_void_p)]),
     "jv_estimator_destroy": (None, [c_void_p]),
     "jv_estimator_set_weight": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, P_i64, c_int]),

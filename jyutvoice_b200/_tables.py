@@ -8,80 +8,124 @@ import torch
 import torch.nn as nn
 
 
-def _resnet(name, cin):
-    return [
-        (f"{name}.mlp.1.weight", (256, 1024)), (f"{name}.mlp.1.bias", (256,)),
-        (f"{name}.block1.block.0.weight", (256, cin, 3)), (f"{name}.block1.block.0.bias", (256,)),
-        (f"{name}.block1.block.2.weight", (256,)), (f"{name}.block1.block.2.bias", (256,)),
-        (f"{name}.block2.block.0.weight", (256, 256, 3)), (f"{name}.block2.block.0.bias", (256,)),
-        (f"{name}.block2.block.2.weight", (256,)), (f"{name}.block2.block.2.bias", (256,)),
-        (f"{name}.res_conv.weight", (256, cin, 1)), (f"{name}.res_conv.bias", (256,)),
-    ]
+
+N_MID = 12
+N_TBLOCKS = 4
 
 
-def _tblock(name):
-    return [
-        (f"{name}.norm1.weight", (256,)), (f"{name}.norm1.bias", (256,)),
-        (f"{name}.attn1.to_q.weight", (512, 256)), (f"{name}.attn1.to_k.weight", (512, 256)),
-        (f"{name}.attn1.to_v.weight", (512, 256)),
-        (f"{name}.attn1.to_out.0.weight", (256, 512)), (f"{name}.attn1.to_out.0.bias", (256,)),
-        (f"{name}.norm3.weight", (256,)), (f"{name}.norm3.bias", (256,)),
-        (f"{name}.ff.net.0.proj.weight", (1024, 256)), (f"{name}.ff.net.0.proj.bias", (1024,)),
-        (f"{name}.ff.net.2.weight", (256, 1024)), (f"{name}.ff.net.2.bias", (256,)),
-    ]
+def estimator_table(prefix="estimator."):
+    """[(key, shape, kind)], kind in {w (fan-in scaled), b (bias), g (LN gamma), beta}."""
+    t = []
+
+    def lin(name, n_out, n_in, bias=True):
+        t.append((name + ".weight", (n_out, n_in), "w"))
+        if bias:
+            t.append((name + ".bias", (n_out,), "b"))
+
+    def conv(name, c_out, c_in, k):
+        t.append((name + ".weight", (c_out, c_in, k), "w"))
+        t.append((name + ".bias", (c_out,), "b"))
+
+    def ln(name, c):
+        t.append((name + ".weight", (c,), "g"))
+        t.append((name + ".bias", (c,), "beta"))
+
+    def resnet(name, c_in):
+        lin(name + ".mlp.1", 256, 1024)
+        conv(name + ".block1.block.0", 256, c_in, 3)
+        ln(name + ".block1.block.2", 256)
+        conv(name + ".block2.block.0", 256, 256, 3)
+        ln(name + ".block2.block.2", 256)
+        conv(name + ".res_conv", 256, c_in, 1)
+
+    def tblock(name):
+        ln(name + ".norm1", 256)
+        lin(name + ".attn1.to_q", 512, 256, bias=False)
+        lin(name + ".attn1.to_k", 512, 256, bias=False)
+        lin(name + ".attn1.to_v", 512, 256, bias=False)
+        lin(name + ".attn1.to_out.0", 256, 512)
+        ln(name + ".norm3", 256)
+        lin(name + ".ff.net.0.proj", 1024, 256)
+        lin(name + ".ff.net.2", 256, 1024)
+
+    lin("time_mlp.linear_1", 1024, 320)
+    lin("time_mlp.linear_2", 1024, 1024)
+    resnet("down_blocks.0.0", 320)
+    for j in range(N_TBLOCKS):
+        tblock(f"down_blocks.0.1.{j}")
+    conv("down_blocks.0.2", 256, 256, 3)
+    for i in range(N_MID):
+        resnet(f"mid_blocks.{i}.0", 256)
+        for j in range(N_TBLOCKS):
+            tblock(f"mid_blocks.{i}.1.{j}")
+    resnet("up_blocks.0.0", 512)
+    for j in range(N_TBLOCKS):
+        tblock(f"up_blocks.0.1.{j}")
+    conv("up_blocks.0.2", 256, 256, 3)
+    conv("final_block.block.0", 256, 256, 3)
+    ln("final_block.block.2", 256)
+    conv("final_proj", 80, 256, 1)
+    return [(prefix + k, s, kind) for k, s, kind in t]
+
+
+def hift_table():
+    """[(key, shape, kind)], kind adds: wn_g / wn_v (weight-norm pair, g derived from v), alpha (Snake)."""
+    t = []
+
+    def wn_conv_new(name, shape):  # torch.nn.utils.parametrizations.weight_norm keys
+        t.append((name + ".bias", None, "b"))  # shape filled below
+        t.append((name + ".parametrizations.weight.original0", (shape[0], 1, 1), "wn_g"))
+        t.append((name + ".parametrizations.weight.original1", shape, "wn_v"))
+
+    def resblock(name, c, k):
+        for grp in ("convs1", "convs2"):
+            for i in range(3):
+                wn_conv_new(f"{name}.{grp}.{i}", (c, c, k))
+        for grp in ("activations1", "activations2"):
+            for i in range(3):
+                t.append((f"{name}.{grp}.{i}.alpha", (c,), "alpha"))
+
+    t.append(("m_source.l_linear.weight", (1, 9), "w"))
+    t.append(("m_source.l_linear.bias", (1,), "b"))
+    wn_conv_new("conv_pre", (512, 80, 7))
+    for i, (cin, cout, k) in enumerate([(512, 256, 16), (256, 128, 11), (128, 64, 7)]):
+        wn_conv_new(f"ups.{i}", (cin, cout, k))  # ConvTranspose1d weight is [Cin, Cout, K]
+    for i, (c, k) in enumerate([(256, 30), (128, 6), (64, 1)]):
+        t.append((f"source_downs.{i}.weight", (c, 18, k), "w"))
+        t.append((f"source_downs.{i}.bias", (c,), "b"))
+    for i, (c, k) in enumerate([(256, 7), (128, 7), (64, 11)]):
+        resblock(f"source_resblocks.{i}", c, k)
+    for i, c in enumerate([256, 128, 64]):
+        for j, k in enumerate([3, 7, 11]):
+            resblock(f"resblocks.{3 * i + j}", c, k)
+    wn_conv_new("conv_post", (18, 64, 7))
+    for i, cin in zip((0, 2, 4, 6, 8), (80, 512, 512, 512, 512)):  # old-style weight_norm keys
+        t.append((f"f0_predictor.condnet.{i}.bias", (512,), "b"))
+        t.append((f"f0_predictor.condnet.{i}.weight_g", (512, 1, 1), "wn_g"))
+        t.append((f"f0_predictor.condnet.{i}.weight_v", (512, cin, 3), "wn_v"))
+    t.append(("f0_predictor.classifier.weight", (1, 512), "w"))
+    t.append(("f0_predictor.classifier.bias", (1,), "b"))
+    return t
+
+
+
+def _bias_shape(table, idx):
+    # bias of a weight-normed conv: out channels.  ConvTranspose (ups.*) has Cout = shape[1].
+    key = table[idx][0]
+    vshape = table[idx + 2][1]
+    return (vshape[1],) if key.startswith("ups.") else (vshape[0],)
 
 
 def estimator_keys(num_mid_blocks=12, n_blocks=4):
-    t = [("time_mlp.linear_1.weight", (1024, 320)), ("time_mlp.linear_1.bias", (1024,)),
-         ("time_mlp.linear_2.weight", (1024, 1024)), ("time_mlp.linear_2.bias", (1024,))]
-    groups = [("down_blocks.0", 320)] + [(f"mid_blocks.{i}", 256) for i in range(num_mid_blocks)] + [("up_blocks.0", 512)]
-    for name, cin in groups:
-        t += _resnet(name + ".0", cin)
-        for j in range(n_blocks):
-            t += _tblock(f"{name}.1.{j}")
-        if not name.startswith("mid"):
-            t += [(f"{name}.2.weight", (256, 256, 3)), (f"{name}.2.bias", (256,))]
-    t += [("final_block.block.0.weight", (256, 256, 3)), ("final_block.block.0.bias", (256,)),
-          ("final_block.block.2.weight", (256,)), ("final_block.block.2.bias", (256,)),
-          ("final_proj.weight", (80, 256, 1)), ("final_proj.bias", (80,))]
-    return t
-
-
-def _wn(name, vshape, cout):
-    return [(f"{name}.bias", (cout,)),
-            (f"{name}.parametrizations.weight.original0", (vshape[0], 1, 1)),
-            (f"{name}.parametrizations.weight.original1", vshape)]
-
-
-def _resblock(name, c, k):
-    t = []
-    for grp in ("convs1", "convs2"):
-        for i in range(3):
-            t += _wn(f"{name}.{grp}.{i}", (c, c, k), c)
-    for grp in ("activations1", "activations2"):
-        for i in range(3):
-            t.append((f"{name}.{grp}.{i}.alpha", (c,)))
-    return t
+    """[(key, shape)] without the 'estimator.' prefix (CausalConditionalDecoder.state_dict())."""
+    assert (num_mid_blocks, n_blocks) == (N_MID, N_TBLOCKS)
+    return [(k, tuple(s)) for k, s, _ in estimator_table(prefix="")]
 
 
 def hift_keys():
-    t = [("m_source.l_linear.weight", (1, 9)), ("m_source.l_linear.bias", (1,))]
-    t += _wn("conv_pre", (512, 80, 7), 512)
-    for i, (cin, cout, k) in enumerate([(512, 256, 16), (256, 128, 11), (128, 64, 7)]):
-        t += _wn(f"ups.{i}", (cin, cout, k), cout)
-    for i, (c, k) in enumerate([(256, 30), (128, 6), (64, 1)]):
-        t += [(f"source_downs.{i}.weight", (c, 18, k)), (f"source_downs.{i}.bias", (c,))]
-    for i, (c, k) in enumerate([(256, 7), (128, 7), (64, 11)]):
-        t += _resblock(f"source_resblocks.{i}", c, k)
-    for i, c in enumerate([256, 128, 64]):
-        for j, k in enumerate([3, 7, 11]):
-            t += _resblock(f"resblocks.{3 * i + j}", c, k)
-    t += _wn("conv_post", (18, 64, 7), 18)
-    for i, cin in zip((0, 2, 4, 6, 8), (80, 512, 512, 512, 512)):
-        t += [(f"f0_predictor.condnet.{i}.bias", (512,)), (f"f0_predictor.condnet.{i}.weight_g", (512, 1, 1)),
-              (f"f0_predictor.condnet.{i}.weight_v", (512, cin, 3))]
-    t += [("f0_predictor.classifier.weight", (1, 512)), ("f0_predictor.classifier.bias", (1,))]
-    return t
+    """[(key, shape)] of HiFTGenerator.state_dict()."""
+    t = hift_table()
+    return [(k, tuple(s) if s is not None else _bias_shape(t, i)) for i, (k, s, _) in enumerate(t)]
 
 
 def build_param_tree(root, table):

@@ -1,10 +1,12 @@
 // Library-wide C-ABI pieces: error text, launch counter, version, GEMM test hook.
 #include "engine.cuh"
+#include "weights.cuh"
 
 namespace jv {
 static thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launch_count{0};
 std::atomic<uint64_t> g_graph_launches{0};
+std::atomic<uint64_t> g_simt_fallbacks{0};
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 __global__ void cvt_f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long n) {
@@ -21,6 +23,7 @@ int jv_version(void) { return 1; }
 const char* jv_last_error(void) { return g_last_error.c_str(); }
 uint64_t jv_launch_count(void) { return g_launch_count.load(); }
 uint64_t jv_graph_launch_count(void) { return g_graph_launches.load(); }
+uint64_t jv_simt_fallback_count(void) { return g_simt_fallbacks.load(); }
 
 int jv_profile_begin(void) {
   JV_API_BEGIN
@@ -59,15 +62,14 @@ int jv_bench_gemm(int M, int N, int K_tap, int taps, int mode, int iters, double
   Engine eng;
   eng.init(dev, JV_PREC_BF16);
   const int Mp = round_up(M, 128);
-  void *A, *W, *OA, *OL;
-  float *R, *OF, *vec;
-  JV_CUDA(cudaMalloc(&A, (size_t)Mp * K_tap * 2));
-  JV_CUDA(cudaMalloc(&W, (size_t)N * K_tap * taps * 2));
-  JV_CUDA(cudaMalloc(&OA, (size_t)Mp * N * 2));
-  JV_CUDA(cudaMalloc(&OL, (size_t)Mp * N * 2));
-  JV_CUDA(cudaMalloc(&R, (size_t)Mp * N * 4));
-  JV_CUDA(cudaMalloc(&OF, (size_t)Mp * N * 4));
-  JV_CUDA(cudaMalloc(&vec, (size_t)N * 4));
+  DeviceAlloc mem;  // frees on every exit path, error throws included
+  void* A = mem.raw((size_t)Mp * K_tap * 2);
+  void* W = mem.raw((size_t)N * K_tap * taps * 2);
+  void* OA = mem.raw((size_t)Mp * N * 2);
+  void* OL = mem.raw((size_t)Mp * N * 2);
+  float* R = (float*)mem.raw((size_t)Mp * N * 4);
+  float* OF = (float*)mem.raw((size_t)Mp * N * 4);
+  float* vec = (float*)mem.raw((size_t)N * 4);
   JV_CUDA(cudaMemset(A, 0, (size_t)Mp * K_tap * 2));
   JV_CUDA(cudaMemset(W, 0, (size_t)N * K_tap * taps * 2));
   JV_CUDA(cudaMemset(R, 0, (size_t)Mp * N * 4));
@@ -84,9 +86,16 @@ int jv_bench_gemm(int M, int N, int K_tap, int taps, int mode, int iters, double
   if (mode & 16) { g.out_act = OA; g.ldo2 = N; }
   if (mode & 32) g.x_bf16 = 1;  // R / OF buffers are simply over-allocated
   JV_REQUIRE(gemm_tc_supported(g), JV_ERR_INVALID, "shape not supported by the tcgen05 engine");
-  cudaEvent_t e0, e1;
-  JV_CUDA(cudaEventCreate(&e0));
-  JV_CUDA(cudaEventCreate(&e1));
+  struct Events {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } ev;
+  JV_CUDA(cudaEventCreate(&ev.a));
+  JV_CUDA(cudaEventCreate(&ev.b));
+  const cudaEvent_t e0 = ev.a, e1 = ev.b;
   for (int i = 0; i < 3; ++i) eng.gemm(g, 0);
   JV_CUDA(cudaEventRecord(e0, 0));
   for (int i = 0; i < iters; ++i) eng.gemm(g, 0);
@@ -95,8 +104,6 @@ int jv_bench_gemm(int M, int N, int K_tap, int taps, int mode, int iters, double
   float ms = 0.f;
   JV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   *ms_out = ms / iters;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(A); cudaFree(W); cudaFree(OA); cudaFree(OL); cudaFree(R); cudaFree(OF); cudaFree(vec);
   JV_API_END
 }
 
@@ -119,10 +126,11 @@ int jv_test_gemm(int precision, int M, int N, int K, const float* A, const float
     g.out_f32 = C;
     g.ldo = N;
     g.o_rows = M;
+    DeviceAlloc mem;
     bf16 *Ab = nullptr, *Wb = nullptr;
     if (precision == JV_PREC_BF16) {
-      JV_CUDA(cudaMalloc(&Ab, (size_t)M * K * 2));
-      JV_CUDA(cudaMalloc(&Wb, (size_t)N * K * 2));
+      Ab = (bf16*)mem.raw((size_t)M * K * 2);
+      Wb = (bf16*)mem.raw((size_t)N * K * 2);
       cvt_f32_to_bf16_kernel<<<(unsigned)(((long)M * K + 255) / 256), 256, 0, st>>>(A, Ab, (long)M * K);
       JV_LAUNCHED();
       cvt_f32_to_bf16_kernel<<<(unsigned)(((long)N * K + 255) / 256), 256, 0, st>>>(W, Wb, (long)N * K);
@@ -136,8 +144,6 @@ int jv_test_gemm(int precision, int M, int N, int K, const float* A, const float
     }
     eng.gemm(g, st);
     JV_CUDA(cudaStreamSynchronize(st));
-    if (Ab) cudaFree(Ab);
-    if (Wb) cudaFree(Wb);
   } catch (const jv::Error& e) {
     set_last_error(e.what());
     return e.code;

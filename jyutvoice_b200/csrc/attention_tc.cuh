@@ -322,7 +322,7 @@ static inline void launch_attention_tc(TmapCache& cache, const void* qkv, void* 
   lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   lattr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = lattr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
   JV_CUDA(cudaLaunchKernelEx(&cfg, attn::attention_tc_kernel, tm, tmkv, (bf16*)out, 512, row_off, row_len,
                              0.125f * 1.4426950408889634f, chunk));
   JV_LAUNCHED();

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <stdexcept>
@@ -27,6 +28,7 @@ struct Error : public std::runtime_error {
 void set_last_error(const std::string& msg);
 extern std::atomic<uint64_t> g_launch_count;
 extern std::atomic<uint64_t> g_graph_launches;  // CUDA-graph replays of an Euler step (jv_cfm_solve)
+extern std::atomic<uint64_t> g_simt_fallbacks;  // bf16-mode GEMMs that were lowered to the FFMA engine (unsupported tcgen05 shape)
 
 #define JV_CUDA(expr)                                                                              \
   do {                                                                                             \
@@ -75,6 +77,8 @@ struct Arena {
 // cudaFuncSetAttribute is per device: true the first time `site` is asked about the CURRENT device (handles on several
 // devices may live in one process; a process-wide "done" flag would leave the second device without its smem opt-in)
 static inline bool first_use_on_device(unsigned long long& site) {
+  static std::mutex mu;  // handles on several host threads may reach a site at the same time
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
   if (site & (1ull << dev)) return false;
@@ -234,6 +238,7 @@ struct GemmDesc {
   long o_rows;           // out_row must be < o_rows
   int x_bf16;            // tcgen05 engine only: `resid` and `out_f32` point to 16-bit tensors (16-bit residual stream) ...
   int x_in_half, x_out_half;  // ... holding fp16 (11-bit significand, stores saturate) instead of bf16
+  int* sat_flag;         // fp16 stream only: incremented when a stored row may have saturated (row sum of squares >= 65504^2)
   double algo_flops;     // algorithmic FLOPs of this launch (valid frames, true N and K); profiling only
 };
 

@@ -14,6 +14,7 @@ struct Engine {
   int precision = JV_PREC_FP32;
   int num_sms = 148;
   TmapCache tmaps;
+  int* sat_flag = nullptr;   // device counter of possibly saturated fp16 stream rows (estimator handle)
   float* scratch = nullptr;  // fp32 [scratch_rows, 256]: pre-LN values when a fused desc is lowered
   long scratch_rows = 0;
   bool is_bf16() const { return precision == JV_PREC_BF16; }
@@ -90,11 +91,18 @@ struct Engine {
     }
   }
 
-  void gemm(const GemmDesc& g, cudaStream_t st) {
+  void gemm(const GemmDesc& g_in, cudaStream_t st) {
+    GemmDesc g = g_in;
+    if (g.x_out_half) g.sat_flag = sat_flag;
     if (is_bf16()) {
       if (gemm_tc_supported(g)) launch_gemm_tc(g, tmaps, num_sms, st);
       else {
+        // Not silent: an unsupported shape runs ~50x slower on the FFMA engine.  Counted (jv_simt_fallback_count) and
+        // reported once per process; the estimator / HiFT graphs of configs/base.yaml never get here (tests assert 0).
         JV_REQUIRE(!g.x_bf16, JV_ERR_INVALID, "a bf16-stream GEMM must fit the tcgen05 engine");
+        if (g_simt_fallbacks.fetch_add(1, std::memory_order_relaxed) == 0)
+          fprintf(stderr, "jyutvoice_b200: bf16 GEMM M=%d N=%d K_tap=%d taps=%d a_stride=%d does not fit the tcgen05 kernel: "
+                          "running it on the FFMA engine (slow)\n", g.M, g.N, g.K_tap, g.n_taps, g.a_stride);
         gemm_lowered<bf16>(g, st);
       }
     } else {

@@ -43,6 +43,9 @@ struct jv_estimator {
   WeightStore store;
   DeviceAlloc mem;
   bool finalized = false;
+  bool stream_half = true;  // bf16 mode: residual stream stored as fp16 (default) or bf16 (jv_estimator_set_stream_format)
+  int* sat_dev = nullptr;   // device counter: rows of the fp16 stream that may have saturated (GemmDesc::sat_flag)
+  int* sat_host = nullptr;  // pinned copy, refreshed asynchronously at the end of every forward / solve
   int chunk = 0;  // attention chunk mask of streaming=True (decoder.py:950-953); 0 = full context
   cudaStream_t cap_stream = nullptr, cap_stream2 = nullptr;  // private streams used only to capture an Euler step into a CUDA graph
   cudaStream_t aux_stream = nullptr;                         // second half-batch of a split solve (eager steps)
@@ -151,6 +154,11 @@ static void finalize_impl(jv_estimator* h) {
   JV_REQUIRE(h->store.t.size() == 910, JV_ERR_STATE, "expected 910 estimator tensors, got %zu (unexpected keys present)",
              h->store.t.size());
   h->store.t.clear();
+  h->sat_dev = (int*)h->mem.raw(sizeof(int));
+  JV_CUDA(cudaMemset(h->sat_dev, 0, sizeof(int)));
+  JV_CUDA(cudaMallocHost(&h->sat_host, sizeof(int)));
+  *h->sat_host = 0;
+  h->eng.sat_flag = h->sat_dev;
   JV_CUDA(cudaDeviceSynchronize());
   h->finalized = true;
 }
@@ -301,13 +309,14 @@ static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void*
   set_ln1(g, w.ln2, ACT_MISH);
   g.resid = c.b.RES; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
-  g.x_bf16 = xb;        // RES comes from a bf16-output GEMM; X is the fp16 stream
-  g.x_out_half = xb;
+  g.x_bf16 = xb;        // RES comes from a bf16-output GEMM; X is the 16-bit stream (fp16 unless the handle says bf16)
+  g.x_out_half = xb && c.h->stream_half;
   set_ln2(c, g, next_ln);
   e.gemm(g, c.st);
 }
 
-// JYUTVOICE_B200_MLP=0 falls back to the two-launch feed-forward (FF1 + GELU, FF2 + residual + norm)
+// JYUTVOICE_B200_MLP=1 opts in to the fused feed-forward kernel (mlp_tc.cuh); the default is the two-launch
+// feed-forward (FF1 + GELU, FF2 + residual + norm), which is faster today
 static bool use_mlp_fused() {
   static int v = -1;
   if (v < 0) {
@@ -329,10 +338,11 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g = conv_desc(c, w.out, c.b.ATT, nullptr, 1);  // x += to_out(attn) ; LNX = norm3(x)
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
-  g.x_bf16 = g.x_in_half = g.x_out_half = xb;
+  g.x_bf16 = xb;
+  g.x_in_half = g.x_out_half = xb && c.h->stream_half;
   set_ln2(c, g, w.n3);
   e.gemm(g, c.st);
-  if (xb && use_mlp_fused()) {  // FF1 + GELU + FF2 + residual (+ next norm1) in one kernel: the hidden never leaves the SM
+  if (xb && c.h->stream_half && use_mlp_fused()) {  // FF1 + GELU + FF2 + residual (+ next norm1) in one kernel: the hidden never leaves the SM
     const bool to_copy = copy_to != nullptr;
     launch_mlp_fused(e.tmaps, c.b.LNX, w.ff1.W, w.ff1.bias, w.ff2.W, w.ff2.bias, c.b.X, to_copy ? copy_to : c.b.X, to_copy ? 0 : 1,
                      next_ln ? next_ln->g : nullptr, next_ln ? next_ln->b : nullptr, next_ln ? c.b.LNX : nullptr, c.b.frame_row,
@@ -346,7 +356,8 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g = conv_desc(c, w.ff2, c.b.FF, nullptr, 1);  // x += ff(norm3(x)) ; LNX = next norm1(x)
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
-  g.x_bf16 = g.x_in_half = g.x_out_half = xb;
+  g.x_bf16 = xb;
+  g.x_in_half = g.x_out_half = xb && c.h->stream_half;
   if (next_ln) set_ln2(c, g, *next_ln);
   if (copy_to) {
     if (xb) { g.out_f32 = (float*)copy_to; g.x_out_half = 0; }  // bf16 copy for the next conv; X is not read again in this group
@@ -557,6 +568,7 @@ void jv_estimator_destroy(jv_estimator* h) {
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->sat_host) cudaFreeHost(h->sat_host);
   }
   delete h;
 }
@@ -565,6 +577,43 @@ int jv_estimator_set_chunk(jv_estimator* h, int chunk_size) {
   JV_API_BEGIN
   JV_REQUIRE(h && chunk_size >= 0, JV_ERR_INVALID, "bad arguments");
   h->chunk = chunk_size;
+  JV_API_END
+}
+
+int jv_estimator_set_stream_format(jv_estimator* h, int format) {
+  JV_API_BEGIN
+  JV_REQUIRE(h && (format == 0 || format == 1), JV_ERR_INVALID, "format must be 0 (fp16) or 1 (bf16)");
+  h->stream_half = format == 0;
+  JV_API_END
+}
+
+int jv_estimator_saturation_count(jv_estimator* h, int synchronize, int64_t* count) {
+  JV_API_BEGIN
+  JV_REQUIRE(h && h->finalized && count, JV_ERR_INVALID, "bad arguments");
+  if (synchronize) {
+    JV_CUDA(cudaSetDevice(h->eng.device));
+    JV_CUDA(cudaDeviceSynchronize());
+    JV_CUDA(cudaMemcpy(h->sat_host, h->sat_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  *count = *h->sat_host;
+  JV_API_END
+}
+
+int jv_estimator_time_embedding(jv_estimator* h, const float* t_host, int n, float* out, void* stream) {
+  JV_API_BEGIN
+  JV_REQUIRE(h && h->finalized, JV_ERR_STATE, "estimator not finalised");
+  JV_REQUIRE(t_host && out && n >= 1 && n <= 4096, JV_ERR_INVALID, "bad arguments");
+  JV_CUDA(cudaSetDevice(h->eng.device));
+  DeviceAlloc tmp;  // test / inspection hook: scratch is allocated here, not taken from a workspace
+  FwdCtx c;
+  c.h = h;
+  c.st = (cudaStream_t)stream;
+  c.b.tsin = (float*)tmp.raw((size_t)n * 320 * sizeof(float));
+  c.b.th1 = (float*)tmp.raw((size_t)n * 1024 * sizeof(float));
+  c.b.th2 = (float*)tmp.raw((size_t)n * 1024 * sizeof(float));
+  c.b.temb = out;
+  run_time_embedding(c, t_host, n);
+  JV_CUDA(cudaStreamSynchronize(c.st));  // scratch dies with this frame
   JV_API_END
 }
 
@@ -639,6 +688,7 @@ int jv_estimator_forward(jv_estimator* h, int R, int Tmax, const int32_t* lens_h
   const long n = (long)R * 80 * Tmax;
   unpack_output_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(out, c.b.V, 80, c.b.row_off, lens_dev, R, Tmax);
   JV_LAUNCHED();
+  JV_CUDA(cudaMemcpyAsync(h->sat_host, h->sat_dev, sizeof(int), cudaMemcpyDeviceToHost, c.st));
   JV_API_END
 }
 
@@ -789,6 +839,7 @@ int jv_cfm_solve(jv_estimator* h, int B, int Tmax, const int32_t* lens_host, con
   } else if (!(n_timesteps >= 3 && use_graph() && !profile_state().on)) {
     join();
   }
+  JV_CUDA(cudaMemcpyAsync(h->sat_host, h->sat_dev, sizeof(int), cudaMemcpyDeviceToHost, user_st));
   JV_API_END
 }
 

@@ -94,7 +94,7 @@ static const KernelEntry* kernel_table() {
   return t;
 }
 
-static bool use_pdl() {
+bool use_pdl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("JYUTVOICE_B200_PDL");

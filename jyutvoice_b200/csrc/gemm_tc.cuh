@@ -766,6 +766,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       // ---- optional post-LayerNorm of the final value (norm1 / norm3 of the next transformer block)
       if (F_LN2) {
         if (!tile_par) row_sum2(sum2, sq2);
+        // fp16 stream: an element can only have reached +-65504 if the row's sum of squares did (conservative, free)
+        if (XB && g.x_out_half && g.sat_flag && sub_id == 0 && sq2 >= 4.29e9f) atomicAdd(g.sat_flag, 1);
         const float mean2 = sum2 * (1.0f / (float)g.N);
         const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / (float)g.N) - mean2 * mean2, 0.f) + 1e-5f);
         int n_ln = 0;
@@ -845,6 +847,8 @@ struct ProfileState {
   double flops = 0.0;
 };
 ProfileState& profile_state();
+
+bool use_pdl();  // JYUTVOICE_B200_PDL=0 disables programmatic dependent launch for every tcgen05 kernel
 
 // True when the tcgen05 kernel can run this problem (else the caller uses the FFMA engine).
 bool gemm_tc_supported(const GemmDesc& g);

@@ -403,18 +403,21 @@ static void run_f0(const HCtx& c, const float* mel, float* f0) {
   JV_LAUNCHED();
 }
 
+// s_stft (generator.py:371-381, 399-400) -> SST [rows(level 3), 18], activation type; needs fr[3]
+static void run_stft(const HCtx& c, const float* s) {
+  jv_hift* h = c.h;
+  const int rows = c.L.rows_alloc[3];
+  if (h->eng.is_bf16()) hift_stft_kernel<bf16><<<cdiv(rows, 128), 128, 0, c.st>>>((bf16*)c.b.SST, c.b.fr[3], c.sq, rows, s, c.Tmax, h->stft_tb);
+  else hift_stft_kernel<float><<<cdiv(rows, 128), 128, 0, c.st>>>((float*)c.b.SST, c.b.fr[3], c.sq, rows, s, c.Tmax, h->stft_tb);
+  JV_LAUNCHED();
+}
+
 static void run_decode(const HCtx& c, const float* mel, const float* s, float* wav) {
   jv_hift* h = c.h;
   Engine& e = h->eng;
   for (int lv = 0; lv < 4; ++lv) hift_frame_rows(c, lv);
   run_pack_mel(c, mel);
-  // s_stft (generator.py:399-400)
-  {
-    const int rows = c.L.rows_alloc[3];
-    if (e.is_bf16()) hift_stft_kernel<bf16><<<cdiv(rows, 128), 128, 0, c.st>>>((bf16*)c.b.SST, c.b.fr[3], c.sq, rows, s, c.Tmax, h->stft_tb);
-    else hift_stft_kernel<float><<<cdiv(rows, 128), 128, 0, c.st>>>((float*)c.b.SST, c.b.fr[3], c.sq, rows, s, c.Tmax, h->stft_tb);
-    JV_LAUNCHED();
-  }
+  run_stft(c, s);
   // conv_pre, then leaky_relu(0.1) for ups[0] (generator.py:402-404)
   {
     GemmDesc g = hconv_desc(c, h->conv_pre, c.b.MEL, 0, 1, 3);
@@ -603,6 +606,22 @@ int jv_hift_source(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const 
   const long n = (long)B * 480 * Tmax;
   hift_source_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(f0, c.b.D, phase, noise, h->src_w, h->src_b, c.b.len, B, Tmax, s,
                                                                     c.Tlong);
+  JV_LAUNCHED();
+  JV_API_END
+}
+
+int jv_hift_stft(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* s, float* out, void* ws, size_t ws_bytes,
+                 void* stream) {
+  JV_API_BEGIN
+  JV_REQUIRE(s && out, JV_ERR_INVALID, "bad arguments");
+  HCtx c;
+  hift_setup(c, h, B, Tmax, lens_host, ws, ws_bytes, stream);
+  hift_frame_rows(c, 3);
+  run_stft(c, s);
+  const int Fmax = 120 * Tmax + 1;
+  const long n = (long)B * 18 * Fmax;
+  if (h->eng.is_bf16()) hift_unpack_stft_kernel<bf16><<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(out, (const bf16*)c.b.SST, c.sq, Fmax);
+  else hift_unpack_stft_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(out, (const float*)c.b.SST, c.sq, Fmax);
   JV_LAUNCHED();
   JV_API_END
 }

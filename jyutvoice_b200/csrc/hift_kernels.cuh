@@ -154,6 +154,17 @@ __global__ void hift_stft_kernel(TA* __restrict__ SST, const int* __restrict__ f
   }
 }
 
+// out[b, k, f] = SST[120 * off_b + f, k] for f < 120 * len_b + 1, else 0  (inspection hook: jv_hift_stft)
+template <typename TA>
+__global__ void hift_unpack_stft_kernel(float* __restrict__ out, const TA* __restrict__ SST, HiftSeq sq, int Fmax) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)sq.B * 18 * Fmax) return;
+  const int f = (int)(idx % Fmax);
+  const int k = (int)((idx / Fmax) % 18);
+  const int b = (int)(idx / ((long)Fmax * 18));
+  out[idx] = f < 120 * sq.len[b] + 1 ? DT<TA>::to_f(SST[(120L * sq.off[b] + f) * 18 + k]) : 0.f;
+}
+
 // ---------------------------------------------------------------- elementwise rows: out = act(in) (fp32 in, TA out)
 template <typename TA>
 __global__ void act_rows_kernel(const float* __restrict__ in, TA* __restrict__ out, long n, int Cn, int act, float p,

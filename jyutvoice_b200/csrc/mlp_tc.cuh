@@ -396,7 +396,7 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
   lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   lattr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = lattr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
   JV_CUDA(cudaLaunchKernelEx(&cfg, mlp::mlp_fused_kernel, tm, p));
   JV_LAUNCHED();
   if (ps.on) {

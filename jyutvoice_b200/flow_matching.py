@@ -62,6 +62,8 @@ class CausalConditionalDecoder(nn.Module):
         if self.precision not in _lib.PREC:
             raise ValueError(f"precision must be one of {list(_lib.PREC)}")
         build_param_tree(self, estimator_keys(num_mid_blocks, n_blocks))
+        self.stream_format = os.environ.get("JYUTVOICE_B200_STREAM", "fp16")
+        self._sat_seen = 0
         self._handle = None
         self._handle_device = None
         self._ws = _Workspace()
@@ -91,27 +93,77 @@ class CausalConditionalDecoder(nn.Module):
             raise RuntimeError("jyutvoice_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         L = _lib.lib()
         h = ctypes.c_void_p()
-        _lib.check(L.jv_estimator_create(device.index or 0, _lib.PREC[self.precision], ctypes.byref(h)))
-        try:
-            _lib.set_weights(h, L.jv_estimator_set_weight, self.state_dict().items())
-            _lib.check(L.jv_estimator_finalize(h))
-        except Exception:
-            L.jv_estimator_destroy(h)
-            raise
+        with torch.cuda.device(device):  # the C ABI selects the handle's device and does not restore the caller's
+            _lib.check(L.jv_estimator_create(device.index or 0, _lib.PREC[self.precision], ctypes.byref(h)))
+            try:
+                _lib.set_weights(h, L.jv_estimator_set_weight, self.state_dict().items())
+                _lib.check(L.jv_estimator_finalize(h))
+                _lib.check(L.jv_estimator_set_stream_format(h, 0 if self.stream_format == "fp16" else 1))
+            except Exception:
+                L.jv_estimator_destroy(h)
+                raise
         self._handle, self._handle_device = h, device
+        self._sat_seen = 0
         return h
+
+    # ---- 16-bit residual stream of bf16 mode
+    def saturation_count(self, synchronize=True):
+        """Rows of the fp16 residual stream that may have reached +-65504 since the handle was built (0 = none can
+        have).  synchronize=False reads the pinned copy of the last completed call without waiting for the device."""
+        if self._handle is None:
+            return 0
+        n = ctypes.c_int64(0)
+        with torch.cuda.device(self._handle_device):
+            _lib.check(_lib.lib().jv_estimator_saturation_count(self._handle, 1 if synchronize else 0, ctypes.byref(n)))
+        return int(n.value)
+
+    def set_stream_format(self, fmt):
+        """"fp16" (default: 11 significand bits, saturating) or "bf16" (fp32 range, 8 bits)."""
+        if fmt not in ("fp16", "bf16"):
+            raise ValueError("stream format must be 'fp16' or 'bf16'")
+        self.stream_format = fmt
+        if self._handle is not None:
+            _lib.check(_lib.lib().jv_estimator_set_stream_format(self._handle, 0 if fmt == "fp16" else 1))
+
+    def _guard_saturation(self):
+        """Called before every launch: if an EARLIER call saturated the fp16 stream (weights with outlier activations),
+        say so once and store the stream as bf16 from now on.  Reads a pinned counter: no device synchronisation."""
+        if self.precision != "bf16" or self.stream_format != "fp16" or self._handle is None:
+            return
+        n = self.saturation_count(synchronize=False)
+        if n > self._sat_seen:
+            import warnings
+            warnings.warn(f"jyutvoice_b200: {n - self._sat_seen} residual-stream rows reached the fp16 range in the previous "
+                          "call; its output may be clipped.  Switching this estimator's stream to bf16.", RuntimeWarning)
+            self._sat_seen = n
+            self.set_stream_format("bf16")
+
+    @torch.inference_mode()
+    def time_embedding(self, t):
+        """Time conditioning of timesteps t [n] -> [n, 14, 256]: row i = resnet i's `mlp(time_mlp(time_embeddings(t)))`
+        (decoder.py:15-30, 127-171, 101-103, 936); the solver computes this table once per solve."""
+        dev = next(self.parameters()).device
+        h = self.handle(dev)
+        tl = [float(v) for v in t.reshape(-1).float().cpu()]
+        out = torch.empty((len(tl), 14, 256), dtype=torch.float32, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().jv_estimator_time_embedding(h, _lib.f32_array(tl), len(tl), ctypes.c_void_p(out.data_ptr()), stream))
+        return out
 
     @torch.inference_mode()
     def forward(self, x, mask, mu, t, spks=None, cond=None, streaming=False):
         """Reference signature (decoder.py:917).  x, mu, cond [R,80,T]; mask [R,1,T]; t [R]; spks [R,80]."""
         dev = x.device
         h = self.handle(dev)
+        self._guard_saturation()
         R, _, T = x.shape
         lens = _lens_from_mask(mask)
         L = _lib.lib()
         lens_c = _lib.i32_array(lens)
-        nbytes = L.jv_cfm_workspace_bytes(h, R, lens_c)
-        ws = self._ws.get(nbytes, dev)
+        with torch.cuda.device(dev):
+            nbytes = L.jv_cfm_workspace_bytes(h, R, lens_c)
+            ws = self._ws.get(nbytes, dev)
         f = lambda z: None if z is None else z.contiguous().float()
         x_, mu_, spks_, cond_ = f(x), f(mu), f(spks), f(cond)
         t_host = _lib.f32_array(t.reshape(-1).float().cpu().tolist() if t.numel() == R else [float(t)] * R)
@@ -167,14 +219,16 @@ class CausalConditionalCFM(nn.Module):
         else:
             lens = _lens_from_mask(mask)
         h = self.estimator.handle(dev)
+        self.estimator._guard_saturation()
         L = _lib.lib()
         lens_c = _lib.i32_array(lens)
         t_span = torch.linspace(0, 1, n_timesteps + 1, dtype=torch.float32)
         if self.t_scheduler == "cosine":
             t_span = 1 - torch.cos(t_span * 0.5 * torch.pi)
         t_c = _lib.f32_array(t_span.tolist())
-        nbytes = L.jv_cfm_solve_workspace_bytes(h, B, lens_c)
-        ws = self._ws.get(nbytes, dev)
+        with torch.cuda.device(dev):
+            nbytes = L.jv_cfm_solve_workspace_bytes(h, B, lens_c)
+            ws = self._ws.get(nbytes, dev)
         mu_ = mu.contiguous().float()
         spks_ = (spks if spks is not None else torch.zeros(B, 80, device=dev)).contiguous().float()
         cond_ = None if cond is None else cond.contiguous().float()

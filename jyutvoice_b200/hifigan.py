@@ -84,13 +84,14 @@ class HiFTGenerator(nn.Module):
             raise RuntimeError("jyutvoice_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         L = _lib.lib()
         h = ctypes.c_void_p()
-        _lib.check(L.jv_hift_create(device.index or 0, _lib.PREC[self.precision], ctypes.byref(h)))
-        try:
-            _lib.set_weights(h, L.jv_hift_set_weight, self.state_dict().items())
-            _lib.check(L.jv_hift_finalize(h))
-        except Exception:
-            L.jv_hift_destroy(h)
-            raise
+        with torch.cuda.device(device):  # the C ABI selects the handle's device and does not restore the caller's
+            _lib.check(L.jv_hift_create(device.index or 0, _lib.PREC[self.precision], ctypes.byref(h)))
+            try:
+                _lib.set_weights(h, L.jv_hift_set_weight, self.state_dict().items())
+                _lib.check(L.jv_hift_finalize(h))
+            except Exception:
+                L.jv_hift_destroy(h)
+                raise
         self._handle, self._handle_device = h, device
         return h
 
@@ -102,7 +103,8 @@ class HiFTGenerator(nn.Module):
         h = self.handle(dev)
         L = _lib.lib()
         lens_c = _lib.i32_array(lens)
-        ws = self._ws.get(L.jv_hift_workspace_bytes(h, B, lens_c), dev)
+        with torch.cuda.device(dev):
+            ws = self._ws.get(L.jv_hift_workspace_bytes(h, B, lens_c), dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         return h, L, lens_c, ws, stream
 
@@ -142,6 +144,22 @@ class HiFTGenerator(nn.Module):
         noise = torch.randn((B, self.nb_harmonics + 1, 480 * T), device=device)
         torch.randn((B, 480 * T, 1), device=device)  # drawn and discarded by the reference; keeps the RNG stream aligned
         return {"phase": phase, "noise": noise}
+
+    @torch.inference_mode()
+    def _stft(self, x, lengths=None):
+        """Reference `_stft` (generator.py:371-381) on s.squeeze(1): x [B, 480T] -> (real, imag), each [B, 9, 120T+1].
+        `lengths` (mel frames): every utterance is reflect-padded at its own end; frames beyond it are 0."""
+        B, L_ = x.shape
+        if L_ % 480 != 0:
+            raise ValueError("the source must hold 480 samples per mel frame")
+        T = L_ // 480
+        dev = x.device
+        h, L, lens_c, ws, stream = self._prep(B, T, lengths, dev)
+        s_ = x.contiguous().float()
+        out = torch.empty((B, 18, 120 * T + 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.jv_hift_stft(h, B, T, lens_c, self._p(s_), self._p(out), self._p(ws), ws.numel(), stream))
+        return out[:, :9], out[:, 9:]
 
     @torch.inference_mode()
     def decode(self, x, s=None, lengths=None):

@@ -19,103 +19,7 @@ import math
 
 import torch
 
-N_MID = 12
-N_TBLOCKS = 4
-
-
-def estimator_table(prefix="estimator."):
-    """[(key, shape, kind)], kind in {w (fan-in scaled), b (bias), g (LN gamma), beta}."""
-    t = []
-
-    def lin(name, n_out, n_in, bias=True):
-        t.append((name + ".weight", (n_out, n_in), "w"))
-        if bias:
-            t.append((name + ".bias", (n_out,), "b"))
-
-    def conv(name, c_out, c_in, k):
-        t.append((name + ".weight", (c_out, c_in, k), "w"))
-        t.append((name + ".bias", (c_out,), "b"))
-
-    def ln(name, c):
-        t.append((name + ".weight", (c,), "g"))
-        t.append((name + ".bias", (c,), "beta"))
-
-    def resnet(name, c_in):
-        lin(name + ".mlp.1", 256, 1024)
-        conv(name + ".block1.block.0", 256, c_in, 3)
-        ln(name + ".block1.block.2", 256)
-        conv(name + ".block2.block.0", 256, 256, 3)
-        ln(name + ".block2.block.2", 256)
-        conv(name + ".res_conv", 256, c_in, 1)
-
-    def tblock(name):
-        ln(name + ".norm1", 256)
-        lin(name + ".attn1.to_q", 512, 256, bias=False)
-        lin(name + ".attn1.to_k", 512, 256, bias=False)
-        lin(name + ".attn1.to_v", 512, 256, bias=False)
-        lin(name + ".attn1.to_out.0", 256, 512)
-        ln(name + ".norm3", 256)
-        lin(name + ".ff.net.0.proj", 1024, 256)
-        lin(name + ".ff.net.2", 256, 1024)
-
-    lin("time_mlp.linear_1", 1024, 320)
-    lin("time_mlp.linear_2", 1024, 1024)
-    resnet("down_blocks.0.0", 320)
-    for j in range(N_TBLOCKS):
-        tblock(f"down_blocks.0.1.{j}")
-    conv("down_blocks.0.2", 256, 256, 3)
-    for i in range(N_MID):
-        resnet(f"mid_blocks.{i}.0", 256)
-        for j in range(N_TBLOCKS):
-            tblock(f"mid_blocks.{i}.1.{j}")
-    resnet("up_blocks.0.0", 512)
-    for j in range(N_TBLOCKS):
-        tblock(f"up_blocks.0.1.{j}")
-    conv("up_blocks.0.2", 256, 256, 3)
-    conv("final_block.block.0", 256, 256, 3)
-    ln("final_block.block.2", 256)
-    conv("final_proj", 80, 256, 1)
-    return [(prefix + k, s, kind) for k, s, kind in t]
-
-
-def hift_table():
-    """[(key, shape, kind)], kind adds: wn_g / wn_v (weight-norm pair, g derived from v), alpha (Snake)."""
-    t = []
-
-    def wn_conv_new(name, shape):  # torch.nn.utils.parametrizations.weight_norm keys
-        t.append((name + ".bias", None, "b"))  # shape filled below
-        t.append((name + ".parametrizations.weight.original0", (shape[0], 1, 1), "wn_g"))
-        t.append((name + ".parametrizations.weight.original1", shape, "wn_v"))
-
-    def resblock(name, c, k):
-        for grp in ("convs1", "convs2"):
-            for i in range(3):
-                wn_conv_new(f"{name}.{grp}.{i}", (c, c, k))
-        for grp in ("activations1", "activations2"):
-            for i in range(3):
-                t.append((f"{name}.{grp}.{i}.alpha", (c,), "alpha"))
-
-    t.append(("m_source.l_linear.weight", (1, 9), "w"))
-    t.append(("m_source.l_linear.bias", (1,), "b"))
-    wn_conv_new("conv_pre", (512, 80, 7))
-    for i, (cin, cout, k) in enumerate([(512, 256, 16), (256, 128, 11), (128, 64, 7)]):
-        wn_conv_new(f"ups.{i}", (cin, cout, k))  # ConvTranspose1d weight is [Cin, Cout, K]
-    for i, (c, k) in enumerate([(256, 30), (128, 6), (64, 1)]):
-        t.append((f"source_downs.{i}.weight", (c, 18, k), "w"))
-        t.append((f"source_downs.{i}.bias", (c,), "b"))
-    for i, (c, k) in enumerate([(256, 7), (128, 7), (64, 11)]):
-        resblock(f"source_resblocks.{i}", c, k)
-    for i, c in enumerate([256, 128, 64]):
-        for j, k in enumerate([3, 7, 11]):
-            resblock(f"resblocks.{3 * i + j}", c, k)
-    wn_conv_new("conv_post", (18, 64, 7))
-    for i, cin in zip((0, 2, 4, 6, 8), (80, 512, 512, 512, 512)):  # old-style weight_norm keys
-        t.append((f"f0_predictor.condnet.{i}.bias", (512,), "b"))
-        t.append((f"f0_predictor.condnet.{i}.weight_g", (512, 1, 1), "wn_g"))
-        t.append((f"f0_predictor.condnet.{i}.weight_v", (512, cin, 3), "wn_v"))
-    t.append(("f0_predictor.classifier.weight", (1, 512), "w"))
-    t.append(("f0_predictor.classifier.bias", (1,), "b"))
-    return t
+from ._tables import estimator_table, hift_table  # noqa: F401  (the single key/shape table)
 
 
 def _bias_shape(table, idx):
@@ -165,9 +69,39 @@ def _draw(table, seed, w_gain=math.sqrt(3.0), g_range=(0.8, 1.2), alpha_range=(0
     return sd
 
 
-def make_estimator_state_dict(seed=1234, prefix="estimator."):
-    """910 fp32 tensors keyed as CausalConditionalCFM.state_dict() (prefix 'estimator.')."""
-    return _draw(estimator_table(prefix), seed)
+def make_estimator_state_dict(seed=1234, prefix="estimator.", init="uniform", scale=1.0):
+    """910 fp32 tensors keyed as CausalConditionalCFM.state_dict() (prefix 'estimator.').
+
+    init="uniform" (default, what the goldens were made with): U(+-sqrt(3/fan_in)) weights, small random biases and
+    LayerNorm affines.  init="reference": what the reference's own constructor leaves behind
+    (decoder.py:414-430 `initialize_weights`: kaiming_normal_(relu) = N(0, 2/fan_in) on every Conv1d / Linear weight,
+    zero biases; LayerNorm at PyTorch's default 1 / 0).  `scale` multiplies every Conv1d / Linear weight (stress sets).
+    """
+    table = estimator_table(prefix)
+    if init == "uniform":
+        sd = _draw(table, seed)
+    elif init == "reference":
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        sd = OrderedDict()
+        for key, shape, kind in table:
+            if kind == "w":
+                fan_in = 1
+                for d in shape[1:]:
+                    fan_in *= d
+                sd[key] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+            elif kind == "g":
+                sd[key] = torch.ones(shape)
+            elif kind in ("b", "beta"):
+                sd[key] = torch.zeros(shape)
+            else:
+                raise ValueError(kind)
+    else:
+        raise ValueError("init must be 'uniform' or 'reference'")
+    if scale != 1.0:
+        for (key, shape, kind) in table:
+            if kind == "w":
+                sd[key] = sd[key] * scale
+    return sd
 
 
 def make_hift_state_dict(seed=4321, f0_bias=None):

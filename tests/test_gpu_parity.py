@@ -3,7 +3,7 @@
  (3) size-independent properties at BASELINE.json's sizes.
 Tolerances (north_star): fp32 mode mel max-abs <= 1e-3, waveform SNR >= 60 dB; integer indexing exact.
 bf16 mode ("stated looser bound", BASELINE.md section 5, frozen from B200 measurements): mel max-abs <= 1e-1 and
-rel-RMS <= 2e-2; waveform SNR >= 40 dB at decode(x, s)."""
+rel-RMS <= 2e-2; waveform SNR >= 45 dB at decode(x, s)."""
 import ctypes
 import os
 
@@ -19,7 +19,7 @@ FP32_MEL_TOL = 1e-3
 BF16_MEL_TOL = 1e-1
 BF16_MEL_RELRMS = 2e-2
 FP32_SNR = 60.0
-BF16_SNR = 40.0
+BF16_SNR = 45.0
 
 
 def rel_rms(x, ref):
@@ -466,3 +466,182 @@ def test_inference_draws_rng_like_the_reference(hifts):
     torch.manual_seed(124)
     w3, _ = hift.inference(mel)
     assert not torch.equal(w1, w3)
+
+
+# ------------------------------------------------------------------------------ headline sizes against the oracle
+def _oracle_cfm_utts(est_sd, noise_bank, lens, mu, spks, idx, nfe):
+    """The oracle (B = 1, unpadded: the reference's only mode) on a few utterances of a batch."""
+    from oracle import estimator as oe
+    out = {}
+    with torch.no_grad():
+        for i in idx:
+            T = lens[i]
+            out[i] = oe.cfm_forward(est_sd, noise_bank, mu[i:i + 1, :, :T], torch.ones(1, 1, T), nfe, 1.0, spks[i:i + 1],
+                                    torch.zeros(1, 80, T))
+    return out
+
+
+@pytest.fixture(scope="module")
+def headline_oracle(est_sd, noise_bank):
+    """bench.py's own batch (BASELINE config 5 per-GPU slice: 64 utterances of 270..330 frames, 10 NFE): the oracle's mel
+    for three of them (~5 s of CPU each), shared by the fp32 and bf16 cases."""
+    from bench import make_workload
+    lens, Tmax, mu, spks = make_workload(64, 300, 1000)
+    idx = (0, 31, 63)
+    return lens, Tmax, mu, spks, _oracle_cfm_utts(est_sd, noise_bank, lens, mu, spks, idx, 10)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_headline_config5_vs_oracle(cfms, prec, headline_oracle):
+    """The benchmarked configuration itself (B = 64, ~300 frames, 10 NFE, CFG): GPU mel against the B = 1 oracle."""
+    lens, Tmax, mu, spks, ref = headline_oracle
+    mel, _ = cfms[prec](mu.cuda(), None, 10, 1.0, spks.cuda(), None, lengths=lens)
+    mel = mel.cpu()
+    assert torch.isfinite(mel).all()
+    for i, r in ref.items():
+        got = mel[i:i + 1, :, : lens[i]]
+        err = (got - r).abs().max().item()
+        if prec == "fp32":
+            assert err <= FP32_MEL_TOL, (i, err)
+        else:
+            assert err <= BF16_MEL_TOL and rel_rms(got, r) <= BF16_MEL_RELRMS, (i, err, rel_rms(got, r))
+        assert float(mel[i, :, lens[i]:].abs().max()) == 0.0
+    if prec == "bf16":
+        assert cfms[prec].estimator.saturation_count() == 0
+
+
+def test_config2_vs_oracle(cfms, est_sd, noise_bank):
+    """BASELINE config 2: batch 16 of ~300 frames, n_timesteps = 10, CFG, bf16 on one GPU; two utterances against the oracle."""
+    from bench import make_workload
+    lens, Tmax, mu, spks = make_workload(16, 300, 2000)
+    ref = _oracle_cfm_utts(est_sd, noise_bank, lens, mu, spks, (3, 12), 10)
+    mel, _ = cfms["bf16"](mu.cuda(), None, 10, 1.0, spks.cuda(), None, lengths=lens)
+    mel = mel.cpu()
+    for i, r in ref.items():
+        got = mel[i:i + 1, :, : lens[i]]
+        assert (got - r).abs().max().item() <= BF16_MEL_TOL and rel_rms(got, r) <= BF16_MEL_RELRMS
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_config3_hift_vs_oracle(hifts, prec, hift_sd):
+    """BASELINE config 3: HiFT alone on 32 mels of 80 x 500; two of them against oracle.decode with the same source."""
+    from oracle import hift as oh
+    hift = hifts[(prec, "unvoiced")]
+    g = torch.Generator().manual_seed(3)
+    mel = torch.randn(32, 80, 500, generator=g) * 2 - 5
+    rng = oh.draw_source_rng(32, 480 * 500, g)
+    wav, s = hift.inference(mel.cuda(), rng=rng)
+    wav, s = wav.cpu(), s.cpu()
+    for i in (1, 30):
+        with torch.no_grad():
+            ref = oh.decode(hift_sd, mel[i:i + 1], s[i:i + 1])
+        assert snr_db(ref, wav[i:i + 1]) >= (FP32_SNR if prec == "fp32" else BF16_SNR)
+
+
+# ------------------------------------------------------------------------------ rows a4 / a9 directly
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_time_embedding_vs_oracle(cfms, prec, est_sd):
+    """SinusoidalPosEmb -> TimestepEmbedding -> per-resnet Mish -> Linear (decoder.py:15-30, 127-171, 101-103), fp32 in
+    both modes: the table the solver builds once per solve."""
+    import torch.nn.functional as F
+    from oracle import estimator as oe
+    t = oe.t_span_cosine(10)[:-1]
+    got = cfms[prec].estimator.time_embedding(t.cuda()).cpu()
+    with torch.no_grad():
+        temb = oe.time_embedding(est_sd, t)
+        names = ["down_blocks.0.0"] + [f"mid_blocks.{i}.0" for i in range(12)] + ["up_blocks.0.0"]
+        ref = torch.stack([F.linear(F.mish(temb), est_sd[f"estimator.{n}.mlp.1.weight"], est_sd[f"estimator.{n}.mlp.1.bias"])
+                           for n in names], dim=1)
+    assert got.shape == ref.shape == (10, 14, 256)
+    assert (got - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["unvoiced", "voiced"])
+def test_stft_golden(hifts, prec, tag):
+    """HiFTGenerator._stft (generator.py:371-381) against the reference's own s_stft; a ragged batch equals the unpadded
+    call (per-utterance reflect padding at the right edge)."""
+    hift = hifts[(prec, tag)]
+    g = np.load(os.path.join(GOLDEN, f"hift_{tag}.npz"))
+    s = torch.from_numpy(g["s"])
+    ref = torch.from_numpy(g["s_stft"])
+    re, im = hift._stft(s.squeeze(1).cuda())
+    got = torch.cat([re, im], dim=1).cpu()
+    assert got.shape == ref.shape
+    tol = 1e-5 if prec == "fp32" else 4e-3 * float(ref.abs().max())  # bf16 mode stores s_stft as the bf16 conv operand
+    assert (got - ref).abs().max().item() <= tol
+    lens = [30, 11]
+    re2, im2 = hift._stft(s.squeeze(1).cuda(), lengths=lens)
+    one_re, one_im = hift._stft(s[1:2, 0, : 480 * 11].contiguous().cuda())
+    assert torch.equal(re2[1:2, :, : 120 * 11 + 1], one_re) and torch.equal(im2[1:2, :, : 120 * 11 + 1], one_im)
+    assert float(re2[1, :, 120 * 11 + 1:].abs().max()) == 0.0
+    assert torch.equal(re2[0], re[0])
+
+
+# ------------------------------------------------------------------------------ 16-bit residual stream under harder weights
+@pytest.mark.parametrize("scale", [1.0, 4.0])
+def test_reference_init_weights_through_bf16_mode(scale, noise_bank):
+    """Weights drawn the way the reference's own constructor does (kaiming-normal, std sqrt(2 / fan_in), zero biases:
+    decoder.py:414-430) and a 4x-scaled stress set: bf16 mode (fp16 residual stream) must stay inside its bound relative
+    to the oracle and must not saturate the stream."""
+    from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, synthetic
+    from oracle import estimator as oe
+    sd = synthetic.make_estimator_state_dict(seed=99, init="reference", scale=scale)
+    cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision="bf16"))
+    cfm.load_state_dict(sd, strict=True)
+    cfm = cfm.cuda()
+    lens = [150, 97]
+    g = torch.Generator().manual_seed(5)
+    mu = torch.randn(2, 80, 150, generator=g)
+    spks = torch.randn(2, 80, generator=g)
+    mel, _ = cfm(mu.cuda(), None, 4, 1.0, spks.cuda(), None, lengths=lens)
+    mel = mel.cpu()
+    with torch.no_grad():
+        ref = oe.cfm_forward_batch(sd, noise_bank, mu, lens, 4, 1.0, spks, None)
+    assert torch.isfinite(mel).all()
+    assert cfm.estimator.saturation_count() == 0
+    scale_ref = max(1.0, float(ref.abs().max()) / 6.0)  # the bound is stated for mels of abs-max ~6 (SURVEY section 7-1)
+    print(f"reference-init x{scale}: ref abs-max {float(ref.abs().max()):.2f}, err {(mel - ref).abs().max().item():.3e}, "
+          f"rel-rms {rel_rms(mel, ref):.3e}")
+    assert (mel - ref).abs().max().item() <= BF16_MEL_TOL * scale_ref and rel_rms(mel, ref) <= BF16_MEL_RELRMS
+
+
+def test_fp16_stream_saturation_is_detected_and_falls_back(noise_bank):
+    """Weights scaled until the fp16 stream clips: the counter must see it, the mirror must warn and switch the stream
+    to bf16 on the next call, and that call must be finite and un-clipped (close to the oracle in relative terms)."""
+    import warnings
+    from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, synthetic
+    from oracle import estimator as oe
+    sd = synthetic.make_estimator_state_dict(seed=99, init="reference", scale=1.0)
+    for k in list(sd):  # blow up the residual branches only: to_out / ff.net.2 write straight into the stream
+        if k.endswith("attn1.to_out.0.weight") or k.endswith("ff.net.2.weight"):
+            sd[k] = sd[k] * 30000.0
+    cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision="bf16"))
+    cfm.load_state_dict(sd, strict=True)
+    cfm = cfm.cuda()
+    g = torch.Generator().manual_seed(6)
+    mu = torch.randn(1, 80, 64, generator=g)
+    spks = torch.randn(1, 80, generator=g)
+    cfm(mu.cuda(), None, 1, 1.0, spks.cuda(), None, lengths=[64])
+    assert cfm.estimator.saturation_count() > 0
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        mel, _ = cfm(mu.cuda(), None, 1, 1.0, spks.cuda(), None, lengths=[64])
+    assert any("bf16" in str(x.message) for x in w)
+    assert cfm.estimator.stream_format == "bf16"
+    with torch.no_grad():
+        ref = oe.cfm_forward(sd, noise_bank, mu, torch.ones(1, 1, 64), 1, 1.0, spks, torch.zeros(1, 80, 64))
+    assert torch.isfinite(mel).all()
+    assert rel_rms(mel.cpu(), ref) <= 5e-2
+
+
+def test_no_ffma_fallback_in_bf16_mode(cfms, hifts):
+    """bf16 mode must run every contraction of both graphs on the tcgen05 kernel: an unsupported shape would be lowered to
+    the FFMA engine (~50x slower) and counted."""
+    from jyutvoice_b200 import _lib
+    L = _lib.lib()
+    n0 = L.jv_simt_fallback_count()
+    mu = torch.randn(2, 80, 70, generator=torch.Generator().manual_seed(4)).cuda()
+    mel, _ = cfms["bf16"](mu, None, 2, spks=torch.zeros(2, 80).cuda(), lengths=[70, 33])
+    hifts[("bf16", "voiced")].inference(mel, lengths=[70, 33])
+    assert L.jv_simt_fallback_count() == n0
