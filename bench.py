@@ -3,7 +3,7 @@
 path on synthetic utterances of BASELINE.json's throughput config (batch 64 per GPU, ~6 s each, bf16).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (torchrun for N > 1)
-  python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the oracle port on host cores
+  python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the reference's own modules (oracle/_ref) on host cores
 
 One "step" = one pass of the hot path over one batch: CausalConditionalCFM.forward -> HiFTGenerator.inference.
 Prints ONE JSON line (rank 0).
@@ -113,17 +113,49 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_pass(est_sd, hift_sd, noise_bank, frames, nfe, seed):
-    """One utterance through the oracle port (B=1, the reference's only mode); returns audio seconds."""
-    from oracle import estimator as oe, hift as oh
-    g = torch.Generator().manual_seed(seed)
-    mu = torch.randn(1, 80, frames, generator=g)
-    spks = torch.randn(1, 80, generator=g)
-    with torch.no_grad():
-        mel = oe.cfm_forward(est_sd, noise_bank, mu, torch.ones(1, 1, frames), nfe, 1.0, spks, torch.zeros(1, 80, frames))
-        rng = oh.draw_source_rng(1, 480 * frames, g)
-        oh.inference(hift_sd, mel, rng)
-    return frames / FRAMES_PER_SEC
+class CpuArm:
+    """The reference's CPU implementation of the path, batch-1 loop (its only mode), fp32, torch CPU threads.
+    kind "reference": the reference's own modules imported from oracle/_ref (byte-compiled from /root/reference by
+    oracle/build_ref.py; the source tree itself when it is present) through oracle/ref_shims.py.
+    kind "port": the oracle restatement (oracle/estimator.py, oracle/hift.py), used only when oracle/_ref is absent."""
+
+    def __init__(self, est_sd, hift_sd):
+        from jyutvoice_b200 import synthetic
+        self.kind = "port"
+        self.est_sd, self.hift_sd = est_sd, hift_sd
+        self.nb = synthetic.noise_bank()
+        try:
+            from oracle import ref_shims
+            if ref_shims.reference_available():
+                self.cfm = ref_shims.build_reference_cfm()
+                self.cfm.load_state_dict(est_sd, strict=True)
+                self.hift = ref_shims.build_reference_hift()
+                self.hift.load_state_dict(hift_sd, strict=True)
+                self.kind = "reference"
+        except Exception as e:  # fall back to the port, and say why
+            print(f"bench.py: reference arm falls back to the oracle port ({type(e).__name__}: {e})", file=sys.stderr)
+            self.kind = "port"
+
+    def one_utterance(self, frames, nfe, seed):
+        """CFM solve + HiFT inference of one synthetic utterance; returns its audio seconds."""
+        g = torch.Generator().manual_seed(seed)
+        mu = torch.randn(1, 80, frames, generator=g)
+        spks = torch.randn(1, 80, generator=g)
+        if self.kind == "reference":
+            with torch.inference_mode():
+                mel, _ = self.cfm(mu, torch.ones(1, 1, frames), nfe, 1.0, spks, torch.zeros(1, 80, frames))
+                self.hift.inference(speech_feat=mel)
+        else:
+            from oracle import estimator as oe, hift as oh
+            with torch.no_grad():
+                mel = oe.cfm_forward(self.est_sd, self.nb, mu, torch.ones(1, 1, frames), nfe, 1.0, spks, torch.zeros(1, 80, frames))
+                oh.inference(self.hift_sd, mel, oh.draw_source_rng(1, 480 * frames, g))
+        return frames / FRAMES_PER_SEC
+
+    def describe(self, n_utts, frames, nfe, cores):
+        what = "the reference's own modules (oracle/_ref)" if self.kind == "reference" else "oracle port"
+        return (f"{n_utts} utterance(s) of {frames} frames, {what}, batch-1 loop (the reference's only mode), fp32, "
+                f"{nfe} NFE + HiFT, torch CPU with {cores} threads")
 
 
 def run_reference(args):
@@ -133,42 +165,88 @@ def run_reference(args):
     from jyutvoice_b200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    est_sd = synthetic.make_estimator_state_dict()
-    hift_sd = synthetic.make_hift_state_dict()
-    nb = synthetic.noise_bank()
+    arm = CpuArm(synthetic.make_estimator_state_dict(), synthetic.make_hift_state_dict())
     for w in range(args.warmup):
-        cpu_reference_pass(est_sd, hift_sd, nb, min(args.frames, 100), args.nfe, w)
-    t0 = time.perf_counter()
+        arm.one_utterance(min(args.frames, 100), args.nfe, w)
+    times = []
     audio = 0.0
     for k in range(args.steps):
-        audio += cpu_reference_pass(est_sd, hift_sd, nb, args.frames, args.nfe, 100 + k)
-    dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        audio += arm.one_utterance(args.frames, args.nfe, 100 + k)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times)
     value = audio / dt
-    sample = f"{args.steps} utterance(s) of {args.frames} frames, batch 1 loop (the reference's only mode), fp32, {args.nfe} NFE + HiFT"
+    sample = arm.describe(args.steps, args.frames, args.nfe, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(1, args.steps), "p50_ms": sorted(times)[len(times) // 2] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "fp32"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args):
+def workload_config(args, precision=None):
     return {"workload": f"BASELINE configs[4] per-GPU slice: batch {args.batch} utterances x ~{args.frames / FRAMES_PER_SEC:.0f} s "
                         f"({int(args.frames * 0.9)}..{int(args.frames * 1.1)} mel frames), n_timesteps={args.nfe}, CFG 0.7, "
                         f"CFM solve + HiFT vocoder",
-            "batch_per_gpu": args.batch, "frames": args.frames, "n_timesteps": args.nfe, "precision": args.precision,
+            "batch_per_gpu": args.batch, "frames": args.frames, "n_timesteps": args.nfe, "precision": precision or args.precision,
             "l2": "no explicit flush: per-step working set (185 MB bf16 weights + >1 GB activations) exceeds the 126 MB L2",
             "weights": "random-init (jyutvoice_b200.synthetic, PyTorch-default statistics)"}
 
 
+def global_workload(world, batch, frames):
+    """BASELINE config 5: a fixed set of 512 synthetic utterances, 64 per GPU.  Slice r of the set is
+    make_workload(batch, frames, 1000 + r); a run on `world` GPUs takes the first `world` slices and shards them with
+    sharding.shard_utterances (at world = 1 that is exactly slice 0 in its own order)."""
+    lens, mus, spk = [], [], []
+    Tmax = int(frames * 1.1)
+    for r in range(world):
+        l, _, mu, sp = make_workload(batch, frames, 1000 + r)
+        lens += l
+        mus.append(mu)
+        spk.append(sp)
+    return lens, Tmax, torch.cat(mus), torch.cat(spk)
+
+
+def p50(xs):
+    s = sorted(xs)
+    return s[len(s) // 2]
+
+
+def small_latency(precision, est_sd, hift_sd, dev, frames=99, nfe=10, reps=7):
+    """BASELINE config 1 (one ~2 s utterance, batch 1, 10 NFE): p50 wall latency of CFM + HiFT through the Python API,
+    host tensors in, waveform back on the host."""
+    from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, HiFTGenerator
+    cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision=precision))
+    cfm.load_state_dict(est_sd, strict=True)
+    cfm = cfm.to(dev)
+    hift = HiFTGenerator(precision=precision)
+    hift.load_state_dict(hift_sd, strict=True)
+    hift = hift.to(dev)
+    g = torch.Generator().manual_seed(0)
+    mu = torch.randn(1, 80, frames, generator=g).pin_memory()
+    spks = torch.randn(1, 80, generator=g).pin_memory()
+    out = torch.empty((1, 480 * frames)).pin_memory()
+    ts = []
+    for i in range(reps + 2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mel, _ = cfm(mu.to(dev, non_blocking=True), None, nfe, 1.0, spks.to(dev, non_blocking=True), None, lengths=[frames])
+        wav, _ = hift.inference(mel, lengths=[frames])
+        out.copy_(wav, non_blocking=True)
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append((time.perf_counter() - t0) * 1e3)
+    return p50(ts)
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, HiFTGenerator, synthetic, _lib
+    from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, HiFTGenerator, synthetic, sharding, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,18 +268,25 @@ def run_ours(args):
     hift.load_state_dict(hift_sd, strict=True)
     hift = hift.to(dev)
 
-    lens, Tmax, mu_h, spks_h = make_workload(args.batch, args.frames, 1000 + rank)
+    # the sweep's utterance set, sharded across the ranks (weak scaling: 64 utterances per GPU)
+    all_lens, Tmax, all_mu, all_spks = global_workload(world, args.batch, args.frames)
+    total = len(all_lens)
+    plan = sharding.shard_utterances(all_lens, world)
+    mine = plan[rank]
+    lens = [all_lens[i] for i in mine]
     audio_s = sum(lens) / FRAMES_PER_SEC
-    mu_pin, spks_pin = mu_h.pin_memory(), spks_h.pin_memory()
+    mu_pin, spks_pin = all_mu[mine].contiguous().pin_memory(), all_spks[mine].contiguous().pin_memory()
+    del all_mu, all_spks
     mu_d, spks_d = mu_pin.to(dev), spks_pin.to(dev)
-    wav_pin = torch.empty((args.batch, 480 * Tmax), dtype=torch.float32).pin_memory()
-    gather_buf = [torch.empty((args.batch, 480 * Tmax), dtype=torch.float32, device=dev) for _ in range(world)] if world > 1 else None
+    n_mine = len(mine)
+    wav_pin = torch.empty((n_mine, 480 * Tmax), dtype=torch.float32).pin_memory()
+    wav_lens = torch.tensor([480 * l for l in lens], dtype=torch.int64, device=dev)
 
     def step(mu, spks):
         mel, _ = cfm(mu, None, args.nfe, 1.0, spks, None, lengths=lens)
         wav, _ = hift.inference(mel, lengths=lens)
-        if world > 1:  # the only collective of the path: gather the waveforms
-            dist.all_gather(gather_buf, wav)
+        if world > 1:  # the only collective of the path: every rank ends up with all waveforms, in the set's order
+            sharding.gather_waveforms(wav, wav_lens, mine, total, 480 * Tmax)
         return wav
 
     def barrier():
@@ -213,31 +298,35 @@ def run_ours(args):
         step(mu_d, spks_d)
     barrier()
 
-    # ---- timed region 1: device-resident inputs (value)
+    # ---- timed region 1: device-resident inputs (value); one event per step boundary gives the per-step p50
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = L.jv_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
-    e0.record()
-    for _ in range(args.steps):
+    evs[0].record()
+    for k in range(args.steps):
         step(mu_d, spks_d)
-    e1.record()
+        evs[k + 1].record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     launches = L.jv_launch_count() - launches0
 
     # ---- timed region 2: end to end through the public API with host buffers (e2e)
     barrier()
-    t0 = time.perf_counter()
+    e2e_ms = []
+    t_all = time.perf_counter()
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         mu = mu_pin.to(dev, non_blocking=True)
         spks = spks_pin.to(dev, non_blocking=True)
         wav = step(mu, spks)
         wav_pin.copy_(wav, non_blocking=True)
         torch.cuda.synchronize()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
     barrier()
-    ms_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = (time.perf_counter() - t_all) * 1e3
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -259,6 +348,10 @@ def run_ours(args):
                 "traffic_source": traffic_src, "peak_source": peaks["src"] + " sustained bf16",
                 "launches_per_step": kn.value / nprof, "kernel_ms_per_step": kms.value / nprof,
                 "algo_tflop_per_step": kfl.value / nprof / 1e12, "share_of_step": (kms.value / nprof) / (ms / args.steps)}
+        # whole-step view: algorithmic FLOPs of the step (BASELINE.md section 4 formulas) over the step time
+        step_tflop = (args.nfe * 2 * sum(132161536.0 * t + 114688.0 * t * t for t in lens) + 612304320.0 * sum(lens)) / 1e12
+        roof["step_algo_tflop"] = step_tflop
+        roof["step_frac"] = step_tflop / (ms / args.steps * 1e-3) / peaks["bf16_sustained"]
 
     # max over ranks, sum of audio
     if world > 1:
@@ -276,29 +369,60 @@ def run_ours(args):
         e2e_value = audio_total * args.steps / (ms_e2e * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "p50_ms": p50(step_ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mu_pin.numel() * 4 + spks_pin.numel() * 4,
-                    "d2h_bytes_per_step": wav_pin.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": wav_pin.numel() * 4, "ms_per_step": ms_e2e / args.steps, "p50_ms": p50(e2e_ms)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "audio_seconds_per_step": audio_total,
+            "utterances_per_step": total,
+            "sharding": "jyutvoice_b200.sharding.shard_utterances over the first 64 x n_gpus of the 512-utterance set; "
+                        "gather_waveforms (NCCL all_gather) inside the timed step" if world > 1 else "single GPU: slice 0 of the set",
         }
         if roof is not None:
             line["roofline"] = roof
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_extra:
+            # (rank 0, single-GPU runs only: the multi-GPU launches stay short)
+            extra = {}
+            del cfm, hift
+            torch.cuda.empty_cache()
+            extra["config1_latency_p50_ms"] = {"workload": "BASELINE configs[0]: one utterance of 99 frames (~2 s), batch 1, 10 NFE, "
+                                                           "CFM + HiFT, host in / host out",
+                                               "bf16": small_latency("bf16", est_sd, hift_sd, dev),
+                                               "fp32": small_latency("fp32", est_sd, hift_sd, dev)}
+            if args.precision == "bf16":  # the <= 1e-3 / >= 60 dB mode on the headline workload: one timed step
+                cfm32 = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision="fp32"))
+                cfm32.load_state_dict(est_sd, strict=True)
+                cfm32 = cfm32.to(dev)
+                hift32 = HiFTGenerator(precision="fp32")
+                hift32.load_state_dict(hift_sd, strict=True)
+                hift32 = hift32.to(dev)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for i in range(2):
+                    if i == 1:
+                        f0.record()
+                    mel, _ = cfm32(mu_d, None, args.nfe, 1.0, spks_d, None, lengths=lens)
+                    hift32.inference(mel, lengths=lens)
+                f1.record()
+                torch.cuda.synchronize()
+                ms32 = f0.elapsed_time(f1)
+                extra["fp32_mode"] = {"value": audio_s / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32, "steps": 1,
+                                      "note": "same workload, precision fp32 (the mel <= 1e-3 / wav >= 60 dB mode)"}
+                del cfm32, hift32
+            line["extra"] = extra
+        if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            nb = synthetic.noise_bank()
-            cpu_reference_pass(est_sd, hift_sd, nb, 100, args.nfe, 0)  # warm-up
+            arm = CpuArm(est_sd, hift_sd)
+            arm.one_utterance(100, args.nfe, 0)  # warm-up
             t0 = time.perf_counter()
             n_utts = 2
-            audio = sum(cpu_reference_pass(est_sd, hift_sd, nb, args.frames, args.nfe, 10 + i) for i in range(n_utts))
+            audio = sum(arm.one_utterance(args.frames, args.nfe, 10 + i) for i in range(n_utts))
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": audio / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_utts} of the {args.batch} utterances ({args.frames} frames each), oracle port, "
-                                              f"batch-1 loop, fp32, torch CPU with {cores} threads"}
+            line["cpu_baseline"] = {"value": audio / dt, "unit": UNIT, "cores": cores, "kind": arm.kind,
+                                    "sample": arm.describe(n_utts, args.frames, args.nfe, cores)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -316,6 +440,7 @@ def main():
     ap.add_argument("--nfe", type=int, default=10)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-1 latency and fp32-mode lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

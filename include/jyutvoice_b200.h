@@ -76,8 +76,8 @@ int jv_estimator_set_chunk(jv_estimator* h, int chunk_size);
 /* bf16 mode stores the residual stream in 16 bits between GEMM epilogues: format 0 = fp16 with saturating stores
  * (default: 11 significand bits), 1 = bf16 (8 bits, fp32 range: for weights whose activations exceed +-65504). */
 int jv_estimator_set_stream_format(jv_estimator* h, int format);
-/* Rows of the fp16 stream whose sum of squares reached 65504^2 since finalize (a conservative test: 0 means no stored
- * value can have saturated).  synchronize = 0 returns the value as of the last completed forward / solve (a pinned
+/* Stores into the fp16 stream that hit the format's largest finite value (+-65504, saturating convert) since finalize,
+ * counted per (row, column share) of a GEMM tile: 0 means nothing was clipped.  synchronize = 0 returns the value as of the last completed forward / solve (a pinned
  * host copy refreshed on the caller's stream); synchronize != 0 waits for the device first. */
 int jv_estimator_saturation_count(jv_estimator* h, int synchronize, int64_t* count);
 /* The time conditioning of n timesteps t (decoder.py:15-30 SinusoidalPosEmb, :127-171 TimestepEmbedding, :101-103 the

@@ -238,7 +238,7 @@ struct GemmDesc {
   long o_rows;           // out_row must be < o_rows
   int x_bf16;            // tcgen05 engine only: `resid` and `out_f32` point to 16-bit tensors (16-bit residual stream) ...
   int x_in_half, x_out_half;  // ... holding fp16 (11-bit significand, stores saturate) instead of bf16
-  int* sat_flag;         // fp16 stream only: incremented when a stored row may have saturated (row sum of squares >= 65504^2)
+  int* sat_flag;         // fp16 stream only: incremented when a value stored into the stream reached +-65504 (saturating convert)
   double algo_flops;     // algorithmic FLOPs of this launch (valid frames, true N and K); profiling only
 };
 

@@ -650,6 +650,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 
       // ---- main pass
       float sum2 = 0.f, sq2 = 0.f;
+      float amax = 0.f;  // largest |value| this thread stores into the 16-bit stream (saturation counter)
       const int n_chunks_valid = (g.N - n0 + 31) / 32 < n_chunks ? (g.N - n0 + 31) / 32 : n_chunks;
       int i_chunk = 0;
       for (int c = c_first; c < ((p.debug & 2) ? 0 : n_chunks_valid); c += c_step, ++i_chunk) {
@@ -719,6 +720,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             acc[j] = __float_as_uint(v[j]);
             sum2 += v[j];
             sq2 = fmaf(v[j], v[j], sq2);
+            if (XB) amax = fmaxf(amax, fabsf(v[j]));
           }
           tmem_st32(taddr + c * 32, acc);
         }
@@ -766,8 +768,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       // ---- optional post-LayerNorm of the final value (norm1 / norm3 of the next transformer block)
       if (F_LN2) {
         if (!tile_par) row_sum2(sum2, sq2);
-        // fp16 stream: an element can only have reached +-65504 if the row's sum of squares did (conservative, free)
-        if (XB && g.x_out_half && g.sat_flag && sub_id == 0 && sq2 >= 4.29e9f) atomicAdd(g.sat_flag, 1);
+        // fp16 stream: count the (row, column-share) pairs in which a stored value reached the format's largest finite number
+        if (XB && g.x_out_half && g.sat_flag && amax >= 65504.f) atomicAdd(g.sat_flag, 1);
         const float mean2 = sum2 * (1.0f / (float)g.N);
         const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / (float)g.N) - mean2 * mean2, 0.f) + 1e-5f);
         int n_ln = 0;

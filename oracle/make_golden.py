@@ -3,7 +3,7 @@
 Run here (the container that has /root/reference):   python -m oracle.make_golden
 The reference cannot travel to the GPU box, so its outputs are committed as small fixtures.
 Inputs are re-derived in the tests from the seeds stored in each file; weights come from
-oracle/weights.py (deterministic) and their fingerprint is stored so a silent RNG difference
+jyutvoice_b200/synthetic.py (deterministic) and their fingerprint is stored so a silent RNG difference
 between machines is detected instead of producing a bogus parity failure.
 """
 import os
@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
-from oracle import ref_shims, weights  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+from jyutvoice_b200 import synthetic as weights  # noqa: E402  (deterministic random-init weights under the reference keys)
 
 OUT = os.path.join(ROOT, "tests", "golden")
 

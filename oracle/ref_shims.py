@@ -25,7 +25,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get("JYUTVOICE_REFERENCE", "/root/reference")
+# Where the reference is imported from: $JYUTVOICE_REFERENCE, else the source tree of this container, else the
+# byte-compiled copy oracle/build_ref.py made from it (oracle/_ref: what travels to the GPU box).
+_BUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_ROOT = os.environ.get("JYUTVOICE_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/jyutvoice") else _BUILT)
 
 
 def reference_available() -> bool:

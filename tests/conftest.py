@@ -26,25 +26,25 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def est_sd():
-    from oracle import weights
+    from jyutvoice_b200 import synthetic as weights
     return weights.make_estimator_state_dict()
 
 
 @pytest.fixture(scope="session")
 def hift_sd():
-    from oracle import weights
+    from jyutvoice_b200 import synthetic as weights
     return weights.make_hift_state_dict()
 
 
 @pytest.fixture(scope="session")
 def hift_sd_voiced():
-    from oracle import weights
+    from jyutvoice_b200 import synthetic as weights
     return weights.make_hift_state_dict(f0_bias=200.0)
 
 
 @pytest.fixture(scope="session")
 def noise_bank():
-    from oracle import weights
+    from jyutvoice_b200 import synthetic as weights
     return weights.noise_bank()
 
 

@@ -598,11 +598,11 @@ def test_reference_init_weights_through_bf16_mode(scale, noise_bank):
     mel = mel.cpu()
     with torch.no_grad():
         ref = oe.cfm_forward_batch(sd, noise_bank, mu, lens, 4, 1.0, spks, None)
-    assert torch.isfinite(mel).all()
-    assert cfm.estimator.saturation_count() == 0
     scale_ref = max(1.0, float(ref.abs().max()) / 6.0)  # the bound is stated for mels of abs-max ~6
     print(f"reference-init x{scale}: ref abs-max {float(ref.abs().max()):.2f}, err {(mel - ref).abs().max().item():.3e}, "
-          f"rel-rms {rel_rms(mel, ref):.3e}")
+          f"rel-rms {rel_rms(mel, ref):.3e}, saturated stores {cfm.estimator.saturation_count()}")
+    assert torch.isfinite(mel).all()
+    assert cfm.estimator.saturation_count() == 0
     assert (mel - ref).abs().max().item() <= BF16_MEL_TOL * scale_ref and rel_rms(mel, ref) <= BF16_MEL_RELRMS
 
 

@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from conftest import GOLDEN, snr_db
-from oracle import estimator as oe, hift as oh, lengths as ol, weights
+from oracle import estimator as oe, hift as oh, lengths as ol
+from jyutvoice_b200 import synthetic as weights
 from oracle.make_golden import est_inputs, cfm_inputs, hift_mel
 
 
