@@ -3,7 +3,8 @@ Skipped where the reference tree is absent (the GPU box)."""
 import pytest
 import torch
 
-from oracle import ref_shims, estimator as oe, hift as oh, weights
+from oracle import ref_shims, estimator as oe, hift as oh
+from jyutvoice_b200 import synthetic as weights
 from conftest import snr_db
 
 pytestmark = pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not present")

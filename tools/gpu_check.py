@@ -60,7 +60,8 @@ def gemms():
 
 
 def estimator_checks():
-    from oracle import weights, estimator as oe
+    from oracle import estimator as oe
+    from jyutvoice_b200 import synthetic as weights
     from oracle.make_golden import est_inputs, cfm_inputs
     from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder
     sd = weights.make_estimator_state_dict()
@@ -117,7 +118,8 @@ def estimator_checks():
 
 
 def hift_checks():
-    from oracle import weights, hift as oh
+    from oracle import hift as oh
+    from jyutvoice_b200 import synthetic as weights
     from oracle.make_golden import hift_mel
     from jyutvoice_b200 import HiFTGenerator
     from conftest import snr_db
