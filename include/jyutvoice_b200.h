@@ -73,8 +73,9 @@ int jv_estimator_finalize(jv_estimator* h);
  * default) restores full context.  State of the handle: applies to every later jv_estimator_forward / jv_cfm_solve. */
 int jv_estimator_set_chunk(jv_estimator* h, int chunk_size);
 
-/* bf16 mode stores the residual stream in 16 bits between GEMM epilogues: format 0 = fp16 with saturating stores
- * (default: 11 significand bits), 1 = bf16 (8 bits, fp32 range: for weights whose activations exceed +-65504). */
+/* bf16 mode stores the residual stream between GEMM epilogues as: format 0 = fp16 with saturating stores (default: 11
+ * significand bits), 1 = bf16 (8 bits, fp32 range), 2 = fp32 (for weights whose activations exceed +-65504: a stream
+ * that large also out-grows 16-bit resolution, so the fallback is fp32, at ~5 % of the throughput). */
 int jv_estimator_set_stream_format(jv_estimator* h, int format);
 /* Stores into the fp16 stream that hit the format's largest finite value (+-65504, saturating convert) since finalize,
  * counted per (row, column share) of a GEMM tile: 0 means nothing was clipped.  synchronize = 0 returns the value as of the last completed forward / solve (a pinned

@@ -7,6 +7,8 @@
 #include "engine.cuh"
 #include "kernels.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc2.cuh"
+#include "attention_tc3.cuh"
 #include "mlp_tc.cuh"
 #include "weights.cuh"
 
@@ -43,7 +45,9 @@ struct jv_estimator {
   WeightStore store;
   DeviceAlloc mem;
   bool finalized = false;
-  bool stream_half = true;  // bf16 mode: residual stream stored as fp16 (default) or bf16 (jv_estimator_set_stream_format)
+  int stream_fmt = 0;       // bf16 mode: residual stream stored as 0 = fp16 (default), 1 = bf16, 2 = fp32 (jv_estimator_set_stream_format)
+  bool stream16() const { return eng.is_bf16() && stream_fmt != 2; }   // the XB epilogue kernels
+  bool stream_half() const { return eng.is_bf16() && stream_fmt == 0; }
   int* sat_dev = nullptr;   // device counter: rows of the fp16 stream that may have saturated (GemmDesc::sat_flag)
   int* sat_host = nullptr;  // pinned copy, refreshed asynchronously at the end of every forward / solve
   int chunk = 0;  // attention chunk mask of streaming=True (decoder.py:950-953); 0 = full context
@@ -167,6 +171,7 @@ static void finalize_impl(jv_estimator* h) {
 struct EstLayout {
   int R = 0, M = 0, M_alloc = 0;
   std::vector<int> row_off, row_len, frame_row;
+  std::vector<int> att_items;  // attention work items (row << 8 | head << 4 | query tile), ordered, non-empty tiles only
 };
 
 static EstLayout make_layout(int R, const int32_t* lens) {
@@ -186,11 +191,15 @@ static EstLayout make_layout(int R, const int32_t* lens) {
   L.frame_row.assign(L.M_alloc, -1);
   for (int r = 0; r < R; ++r)
     for (int t = 0; t < lens[r]; ++t) L.frame_row[L.row_off[r] + t] = r;
+  for (int r = 0; r < R; ++r)
+    for (int h = 0; h < 8; ++h)
+      for (int qt = 0; qt * 128 < lens[r] && qt < 16; ++qt) L.att_items.push_back((r << 8) | (h << 4) | qt);
   return L;
 }
 
 struct EstBuffers {
   int *frame_row, *row_off, *row_len, *row_tidx;
+  int* att_items;  // [n_att_items]
   float* temb;   // [nt, 14, 256]
   float* tsin;   // [nt, 320]
   float* th1;    // [nt, 1024]
@@ -206,6 +215,7 @@ static EstBuffers carve(Arena& ar, const Engine& eng, int M_alloc, int R, int nt
   b.row_off = ar.alloc<int>(R + 1);
   b.row_len = ar.alloc<int>(R);
   b.row_tidx = ar.alloc<int>(R);
+  b.att_items = ar.alloc<int>((size_t)(M_alloc / 128 + R) * 8);  // sum over rows of ceil(len / 128) <= M_alloc / 128 + R
   b.temb = ar.alloc<float>((size_t)nt * N_RESNET * C);
   b.tsin = ar.alloc<float>((size_t)nt * 320);
   b.th1 = ar.alloc<float>((size_t)nt * 1024);
@@ -231,6 +241,7 @@ struct FwdCtx {
   jv_estimator* h;
   EstBuffers b;
   int M, M_alloc, R, Tmax_len;  // Tmax_len: longest row (attention grid)
+  int n_att_items;
   long valid_frames;            // sum of row lengths (algorithmic FLOP accounting)
   const float* temb_step;       // temb rows of the current step: [*, 14, 256]
   cudaStream_t st;
@@ -262,7 +273,8 @@ static GemmDesc conv_desc(const FwdCtx& c, const PackedW& w, const void* A0p, co
 
 static void run_attention(const FwdCtx& c) {
   if (c.h->eng.is_bf16()) {  // tcgen05 flash-style kernel
-    launch_attention_tc(c.h->eng.tmaps, c.b.QKV, c.b.ATT, c.b.row_off, c.b.row_len, c.M_alloc, c.R, c.Tmax_len, c.h->chunk, c.st);
+    launch_attention(c.h->eng.tmaps, c.b.QKV, c.b.ATT, c.b.row_off, c.b.row_len, c.b.att_items, c.n_att_items, c.M_alloc, c.R,
+                     c.Tmax_len, c.h->chunk, c.h->eng.num_sms, c.st);
     return;
   }
   static unsigned long long attr = 0;
@@ -298,8 +310,8 @@ static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void*
   g.add_row_stride = N_RESNET * C;
   g.out_act = c.b.H; g.ldo2 = C;
   e.gemm(g, c.st);
-  // res_conv(x*m) -> RES (bf16 mode: the residual stream X / RES is bf16)
-  const bool xb = e.is_bf16();
+  // res_conv(x*m) -> RES (bf16 mode: the residual stream X / RES is 16-bit unless the handle asks for fp32)
+  const bool xb = c.h->stream16();
   g = conv_desc(c, w.res, in0, in1, 1);
   if (xb) { g.out_act = c.b.RES; g.ldo2 = C; }
   else { g.out_f32 = c.b.RES; g.ldo = C; }
@@ -310,7 +322,7 @@ static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void*
   g.resid = c.b.RES; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
   g.x_bf16 = xb;        // RES comes from a bf16-output GEMM; X is the 16-bit stream (fp16 unless the handle says bf16)
-  g.x_out_half = xb && c.h->stream_half;
+  g.x_out_half = c.h->stream_half();
   set_ln2(c, g, next_ln);
   e.gemm(g, c.st);
 }
@@ -334,15 +346,15 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g.out_act = c.b.QKV; g.ldo2 = 1536;
   e.gemm(g, c.st);
   run_attention(c);
-  const bool xb = e.is_bf16();
+  const bool xb = c.h->stream16();
   g = conv_desc(c, w.out, c.b.ATT, nullptr, 1);  // x += to_out(attn) ; LNX = norm3(x)
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
   g.x_bf16 = xb;
-  g.x_in_half = g.x_out_half = xb && c.h->stream_half;
+  g.x_in_half = g.x_out_half = c.h->stream_half();
   set_ln2(c, g, w.n3);
   e.gemm(g, c.st);
-  if (xb && c.h->stream_half && use_mlp_fused()) {  // FF1 + GELU + FF2 + residual (+ next norm1) in one kernel: the hidden never leaves the SM
+  if (c.h->stream_half() && use_mlp_fused()) {  // FF1 + GELU + FF2 + residual (+ next norm1) in one kernel: the hidden never leaves the SM
     const bool to_copy = copy_to != nullptr;
     launch_mlp_fused(e.tmaps, c.b.LNX, w.ff1.W, w.ff1.bias, w.ff2.W, w.ff2.bias, c.b.X, to_copy ? copy_to : c.b.X, to_copy ? 0 : 1,
                      next_ln ? next_ln->g : nullptr, next_ln ? next_ln->b : nullptr, next_ln ? c.b.LNX : nullptr, c.b.frame_row,
@@ -357,7 +369,7 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g.resid = c.b.X; g.ldr = C;
   g.out_f32 = c.b.X; g.ldo = C;
   g.x_bf16 = xb;
-  g.x_in_half = g.x_out_half = xb && c.h->stream_half;
+  g.x_in_half = g.x_out_half = c.h->stream_half();
   if (next_ln) set_ln2(c, g, *next_ln);
   if (copy_to) {
     if (xb) { g.out_f32 = (float*)copy_to; g.x_out_half = 0; }  // bf16 copy for the next conv; X is not read again in this group
@@ -446,6 +458,7 @@ static void upload_layout(const FwdCtx& c, const EstLayout& L, const std::vector
   JV_CUDA(cudaMemcpyAsync(c.b.row_off, L.row_off.data(), L.row_off.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
   JV_CUDA(cudaMemcpyAsync(c.b.row_len, L.row_len.data(), L.row_len.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
   JV_CUDA(cudaMemcpyAsync(c.b.row_tidx, tidx.data(), tidx.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  JV_CUDA(cudaMemcpyAsync(c.b.att_items, L.att_items.data(), L.att_items.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
   JV_CUDA(cudaStreamSynchronize(c.st));  // host vectors die with the caller's frame
 }
 
@@ -512,6 +525,7 @@ static void carve_part(SolvePart& pt, jv_estimator* h, Arena& ar, const int32_t*
   pt.lens_dev = ar.alloc<int>(R);
   pt.dts_dev = ar.alloc<float>(64);
   pt.c.M = L.M; pt.c.M_alloc = L.M_alloc; pt.c.R = R; pt.c.Tmax_len = tl;
+  pt.c.n_att_items = (int)L.att_items.size();
   pt.c.valid_frames = 0;
   for (int r = 0; r < R; ++r) pt.c.valid_frames += L.row_len[r];
   if (tmax_len) *tmax_len = tl;
@@ -580,10 +594,15 @@ int jv_estimator_set_chunk(jv_estimator* h, int chunk_size) {
   JV_API_END
 }
 
+int jv_debug_attention_trace(void* buf) {  // development aid, not part of include/jyutvoice_b200.h
+  attention_trace_buffer() = (long long*)buf;
+  return JV_OK;
+}
+
 int jv_estimator_set_stream_format(jv_estimator* h, int format) {
   JV_API_BEGIN
-  JV_REQUIRE(h && (format == 0 || format == 1), JV_ERR_INVALID, "format must be 0 (fp16) or 1 (bf16)");
-  h->stream_half = format == 0;
+  JV_REQUIRE(h && format >= 0 && format <= 2, JV_ERR_INVALID, "format must be 0 (fp16), 1 (bf16) or 2 (fp32)");
+  h->stream_fmt = format;
   JV_API_END
 }
 
@@ -674,6 +693,7 @@ int jv_estimator_forward(jv_estimator* h, int R, int Tmax, const int32_t* lens_h
   c.b = carve(ar, h->eng, L.M_alloc, R, R);
   int* lens_dev = ar.alloc<int>(R);
   c.M = L.M; c.M_alloc = L.M_alloc; c.R = R; c.Tmax_len = tmax_len;
+  c.n_att_items = (int)L.att_items.size();
   c.valid_frames = 0;
   for (int r = 0; r < R; ++r) c.valid_frames += L.row_len[r];
   c.st = (cudaStream_t)stream;

@@ -71,25 +71,26 @@ typedef void (*KernelFn)(const tc::TcMaps, const GemmDesc, const tc::TcParams);
 struct KernelEntry {
   int epi;
   KernelFn fn;
+  KernelFn fn_pair;  // cta_group::2 variant of the same epilogue
 };
 constexpr int N_KERNELS = 12;
 // the epilogue shapes the estimator / HiFT graphs actually use, plus the run-time generic kernel (last)
 static const KernelEntry* kernel_table() {
   using namespace tc;
   static const KernelEntry t[N_KERNELS] = {
-      {EPI_OACT, gemm_taps_tc_kernel<EPI_OACT>},                                              // QKV, FF1, plain convs
-      {EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_LN2>},    // out-proj, FF2 (+ next norm)
-      {EPI_RESID | EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_OACT>},  // last FF2 of a group, HiFT conv2
-      {EPI_LN1 | EPI_OACT, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT>},                          // CausalBlock1D (block1, final_block)
-      {EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>},  // block2 + res + norm1
-      {EPI_F32, gemm_taps_tc_kernel<EPI_F32>},                                                // res_conv, final_proj, conv_post
-      {EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_RESID | EPI_F32>},                        // HiFT ups + source, last conv2
-      {EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_F32 | EPI_OACT>},                          // HiFT source_downs (im2col)
+      {EPI_OACT, gemm_taps_tc_kernel<EPI_OACT>, gemm_taps_tc_kernel<EPI_OACT, true>},                                              // QKV, FF1, plain convs
+      {EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_LN2, true>},    // out-proj, FF2 (+ next norm)
+      {EPI_RESID | EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_OACT>, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_OACT, true>},  // last FF2 of a group, HiFT conv2
+      {EPI_LN1 | EPI_OACT, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT>, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT, true>},                          // CausalBlock1D (block1, final_block)
+      {EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, true>},  // block2 + res + norm1
+      {EPI_F32, gemm_taps_tc_kernel<EPI_F32>, gemm_taps_tc_kernel<EPI_F32, true>},                                                // res_conv, final_proj, conv_post
+      {EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_RESID | EPI_F32>, gemm_taps_tc_kernel<EPI_RESID | EPI_F32, true>},                        // HiFT ups + source, last conv2
+      {EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_F32 | EPI_OACT>, gemm_taps_tc_kernel<EPI_F32 | EPI_OACT, true>},                          // HiFT source_downs (im2col)
       // bf16 residual stream (estimator, bf16 mode)
-      {EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2>},
-      {EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>},
-      {EPI_XB | EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32>},
-      {-1, gemm_taps_tc_kernel<-1>},
+      {EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, true>},
+      {EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, true>},
+      {EPI_XB | EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32>, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32, true>},
+      {-1, gemm_taps_tc_kernel<-1>, gemm_taps_tc_kernel<-1, true>},
   };
   return t;
 }
@@ -140,6 +141,16 @@ static bool use_wres() {
   return v == 1;
 }
 
+// JYUTVOICE_B200_PAIR=0: no cta_group::2 CTA pairs (every MMA is cta_group::1, M = 128)
+static bool use_pair() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 bool gemm_tc_supported(const GemmDesc& g) {
@@ -173,8 +184,10 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   if (g.M <= 0 || g.N <= 0) return;
   static unsigned long long attr_set = 0;
   if (first_use_on_device(attr_set)) {
-    for (int i = 0; i < N_KERNELS; ++i)
+    for (int i = 0; i < N_KERNELS; ++i) {
       JV_CUDA(cudaFuncSetAttribute((const void*)kernel_table()[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+      JV_CUDA(cudaFuncSetAttribute((const void*)kernel_table()[i].fn_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+    }
   }
   tc::TcParams p;
   p.block_n = g.N <= 256 ? round_up(g.N, 32) : wide_block_n(g.N);
@@ -210,6 +223,13 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   // weight-resident mode: whole weight tile <= 128 KB, bf16-only epilogue (or slab mode), enough m-tiles per CTA
   const int ctas_per_ntile = num_sms / p.n_tiles_n;
   p.wres = (p.slab || (epi == tc::EPI_OACT && w_fits && ctas_per_ntile >= 1 && (m_tiles >= 4 * ctas_per_ntile || force_modes()) && use_wres())) ? 1 : 0;
+  // CTA pair (cta_group::2, M = 256 over two SMs): for the kernels that stream their weights (not weight-resident, not
+  // slab): each CTA of the pair loads half of the weight tile.  N per instruction must be a multiple of 16.
+  p.pair = (!p.wres && !p.slab && (p.block_n == 256 || p.block_n == 128 || p.block_n == 64) && m_tiles >= 2 && num_sms % 2 == 0 &&
+            cluster_size() == 1 && use_pair())
+               ? 1
+               : 0;
+  if (p.pair) p.b_stage_bytes = round_up((p.block_n / 2) * tc::BLOCK_K * 2, 1024);
   const bool wide = epi == tc::EPI_OACT;  // bf16-only epilogue: 16 epilogue warps, small staging
   const int n_epi_warps = wide ? tc::EPI_WARPS_MAX : tc::EPI_WARPS;
   {  // staging layout per epilogue warp, exactly what this epilogue kind needs
@@ -294,8 +314,8 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   tc::TcMaps tm;
   tm.a0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], (long)g.lda[0] * 2, tc::BLOCK_K, p.slab ? p.slab_rows : tc::BLOCK_M, 0);
   tm.a1 = g.A[1] ? cache.get(g.A[1], g.K_tap, g.a_rows[1], (long)g.lda[1] * 2, tc::BLOCK_K, tc::BLOCK_M, 0) : tm.a0;
-  p.cluster = 1;
-  for (int cs = cluster_size(); cs >= 2; cs >>= 1)
+  p.cluster = p.pair ? 2 : 1;
+  for (int cs = cluster_size(); cs >= 2 && !p.pair; cs >>= 1)
     if (!p.wres && m_tiles >= cs && p.block_n % (8 * cs) == 0 && num_sms % cs == 0) { p.cluster = cs; break; }
   p.num_units = p.wres ? m_tiles : cdiv(m_tiles, p.cluster) * p.n_tiles_n;
   tm.w = cache.get(g.W, Ktot, g.N, Ktot * 2, tc::BLOCK_K, p.block_n / p.cluster, 0);
@@ -328,10 +348,11 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 2 : 1;
-  KernelFn fn = kernel_table()[N_KERNELS - 1].fn;  // generic
+  const KernelEntry* ke = &kernel_table()[N_KERNELS - 1];  // generic
   bool found = false;
   for (int i = 0; i < N_KERNELS - 1; ++i)
-    if (kernel_table()[i].epi == epi) { fn = kernel_table()[i].fn; found = true; }
+    if (kernel_table()[i].epi == epi) { ke = &kernel_table()[i]; found = true; }
+  KernelFn fn = p.pair ? ke->fn_pair : ke->fn;
   JV_REQUIRE(found || !g.x_bf16, JV_ERR_INVALID, "no bf16-stream kernel for epilogue kind %d", epi);
   JV_CUDA(cudaLaunchKernelEx(&cfg, fn, tm, g, p));
   JV_LAUNCHED();

@@ -96,6 +96,36 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster issue ONE M = 256 MMA; each feeds its own 128 activation rows and
+// HALF of the weight tile, so an SM ingests half the weight bytes per flop (the N = 256 kernels are bound by L2 -> SM
+// operand traffic, ~43 B / clk / SM: DESIGN.md section 6).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {  // same smem offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA load whose mbarrier may live in the peer CTA (the leader collects both CTAs' bytes on one barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* tm, uint32_t bar_cluster, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tm), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {  // arrives on `bar`'s offset in every CTA of `mask`
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -269,6 +299,8 @@ struct TcParams {
   int cluster;    // CTAs per cluster (1 or 2): the CTAs of a cluster work on consecutive m-tiles of the same n-tile and
                   // each loads 1/cluster of the weight tile, multicast to all of them (halves the L2 -> SM weight traffic)
   int num_units;  // ceil(m_tiles / cluster) * n_tiles_n   (weight-resident mode: m_tiles)
+  int pair;       // cluster == 2 and the two CTAs form one cta_group::2 MMA (M = 256): each loads half of the weight tile,
+                  // nothing is multicast; only rank 0 issues MMAs, and it collects both CTAs' TMA bytes and epilogue arrivals
   // Weight-resident mode (K_total * block_n * 2 <= 128 KB, bf16-only output: QKV, FF1): a CTA is bound to one n-tile,
   // loads its whole weight tile into smem ONCE and streams only activation tiles through the ring.  The kernel is
   // bound by SM <-> L2 traffic, and the weight tile is 2/3 of a 128 x 256 tile's operand bytes.
@@ -339,7 +371,9 @@ constexpr int EPI_LN1 = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_OACT = 8, EPI_LN2 = 1
 // right after it was issued).  The fp32-stream kernels move twice the bytes with half the loads in flight.
 constexpr int EPI_XB = 32;
 
-template <int EPI>
+// PAIR: the cta_group::2 variant (TcParams::pair).  A separate instantiation, not a run-time switch: a kernel that contains
+// cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration" otherwise).
+template <int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(EPI == EPI_OACT ? NUM_THREADS_WIDE : NUM_THREADS, 1)
 gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const TcParams p) {
   const bool F_LN1 = EPI >= 0 ? (EPI & EPI_LN1) != 0 : g.ln1_gamma != nullptr;
@@ -386,19 +420,24 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(full_bar + 8 * i, 1);
-      mbar_init(empty_bar + 8 * i, csz);
+      mbar_init(empty_bar + 8 * i, PAIR ? 1 : csz);
     }
     for (int i = 0; i < p.n_acc; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, p.tile_par ? 128 : 32 * N_EPI_WARPS);
+      mbar_init(tempty_bar + 8 * i, (PAIR ? 2 : 1) * (p.tile_par ? 128 : 32 * N_EPI_WARPS));
     }
     for (int i = 0; i < 2 * EPI_WARPS_MAX; ++i) mbar_init(epi_bar + 8 * i, 1);
     mbar_init(wres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (p.slab && warp == 3) {  // descriptor tables for the MMA thread: everything that does not depend on the ring stage
     uint64_t* tab = reinterpret_cast<uint64_t*>(smem_raw + (base - raw) + p.tab_off);
@@ -468,6 +507,22 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           }
           continue;
         }
+        if constexpr (PAIR) {  // both CTAs load (own activation rows, own half of the weight tile); all bytes land on the leader's barrier
+          const uint32_t full_leader = mapa_u32(full_bar, 0);
+          for (int s = 0; s < g.n_taps; ++s) {
+            const CUtensorMap* tmA = g.tap_src[s] ? &tm.a1 : &tm.a0;
+            const int arow = m0 + g.tap_shift[s];
+            for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
+              mbar_wait(empty_bar + 8 * stage, phase ^ 1, 1);
+              if (cta_rank == 0) mbar_expect_tx(full_bar + 8 * stage, 2u * (A_STAGE_BYTES + (uint32_t)b_rows * BLOCK_K * 2));
+              tma_load_2d_cg2(tmA, full_leader + 8 * stage, smem_a + stage * p.a_stage_bytes, kb * BLOCK_K, arow);
+              tma_load_2d_cg2(&tm.w, full_leader + 8 * stage, smem_b + stage * p.b_stage_bytes, s * g.K_tap + kb * BLOCK_K,
+                              n0 + cta_rank * b_rows);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int s = 0; s < g.n_taps; ++s) {
           const CUtensorMap* tmA = g.tap_src[s] ? &tm.a1 : &tm.a0;
           const int arow = m0 + g.tap_shift[s];
@@ -488,10 +543,11 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && !(PAIR && cta_rank != 0)) {  // CTA pair: the leader issues for both
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
-      // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)  (M = 256 across the CTA pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc_stage = 0;
@@ -518,6 +574,21 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
           umma_commit(tfull_bar + 8 * acc_stage);
+          if (++acc_stage == p.n_acc) { acc_stage = 0; acc_phase ^= 1; }
+          continue;
+        }
+        if constexpr (PAIR) {
+          for (int it = 0; it < k_iters; ++it) {
+            mbar_wait(full_bar + 8 * stage, phase, 3);  // both CTAs' tiles of this stage have landed
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_a + stage * p.a_stage_bytes);
+            const uint64_t bdesc = make_smem_desc(smem_b + stage * p.b_stage_bytes);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit_cg2(empty_bar + 8 * stage, 3);  // frees the slot in both CTAs
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_cg2(tfull_bar + 8 * acc_stage, 3);  // both CTAs' epilogues own a half of the accumulator
           if (++acc_stage == p.n_acc) { acc_stage = 0; acc_phase ^= 1; }
           continue;
         }
@@ -798,7 +869,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar + 8 * grp);
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar + 8 * grp, 0));  // the leader's MMA thread waits for both halves
+      else mbar_arrive(tempty_bar + 8 * grp);
       if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait0();  // smem must outlive the last TMA store's reads
@@ -809,7 +881,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   if (csz > 1) cluster_sync_all();  // no CTA leaves while a peer can still multicast into it or arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 

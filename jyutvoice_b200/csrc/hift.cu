@@ -121,7 +121,7 @@ static void hift_finalize_impl(jv_hift* h) {
   h->src_w = h->mem.upload_f32(h->store.get("m_source.l_linear.weight", {1, 9}).data);
   h->src_b = h->mem.upload_f32(h->store.get("m_source.l_linear.bias", {1}).data);
   h->conv_pre = hpack_conv(h, "conv_pre", 512, 80, 7, 128, 512);
-  h->conv_post = hpack_conv(h, "conv_post", 18, 64, 7, 64, 32);
+  h->conv_post = hpack_conv(h, "conv_post", 18, 64, 7, 64, SPEC_LD);
   int cin = 512;
   for (int i = 0; i < 3; ++i) {
     UpW& U = h->ups[i];
@@ -222,7 +222,7 @@ struct HiftBuffers {
   float* X[3];                   // per stage: x after ups + source fusion (fp32)
   float* S[3][3];                // per stage: the three ResBlock streams (S[i][0] first carries the source branch)
   void *XT[3], *XT2[3];          // per stage activation-typed conv inputs
-  float* SPEC;                   // [rows2, 32]
+  float* SPEC;                   // [rows2, SPEC_LD]
 };
 
 // `Tlong` = longest utterance of the batch (NOT the caller's tensor stride: jv_hift_workspace_bytes sees only the lengths)
@@ -252,7 +252,7 @@ static HiftBuffers hift_carve(Arena& ar, const Engine& eng, const HiftLayout& L,
     b.XT[i] = ar.alloc<char>(n * es);
     b.XT2[i] = ar.alloc<char>(n * es);
   }
-  b.SPEC = ar.alloc<float>((size_t)L.rows_alloc[3] * 32);
+  b.SPEC = ar.alloc<float>((size_t)L.rows_alloc[3] * SPEC_LD);
   return b;
 }
 
@@ -526,13 +526,13 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
   }
   {
     GemmDesc g = hconv_desc(c, h->conv_post, c.b.P[3], 3, 1, 3);
-    g.algo_flops *= 18.0 / 32.0;
+    g.algo_flops *= 18.0 / SPEC_LD;
     g.out_f32 = c.b.SPEC;
-    g.ldo = 32;
+    g.ldo = SPEC_LD;
     e.gemm(g, c.st);
   }
   dim3 grid(cdiv(480 * c.Tmax, 256), c.L.B);
-  hift_istft_kernel<<<grid, 256, 0, c.st>>>(c.b.SPEC, 32, c.sq, c.Tmax, wav, h->istft_tb, 0.99f);
+  hift_istft_kernel<<<grid, 256, 0, c.st>>>(c.b.SPEC, SPEC_LD, c.sq, c.Tmax, wav, h->istft_tb, 0.99f, (long)c.L.rows_alloc[3]);
   JV_LAUNCHED();
 }
 
@@ -604,7 +604,7 @@ int jv_hift_source(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const 
   hift_phase_prefix_kernel<<<cdiv(B * 9, 64), 64, 0, c.st>>>(f0, Tmax, c.b.len, B, c.b.D, c.Tlong);
   JV_LAUNCHED();
   const long n = (long)B * 480 * Tmax;
-  hift_source_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(f0, c.b.D, phase, noise, h->src_w, h->src_b, c.b.len, B, Tmax, s,
+  hift_source_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, c.st>>>(f0, c.b.D, phase, noise, h->src_w, h->src_b, c.b.len, B, Tmax, s,
                                                                     c.Tlong);
   JV_LAUNCHED();
   JV_API_END

@@ -82,33 +82,55 @@ __global__ void hift_phase_prefix_kernel(const float* __restrict__ f0, int Tmax,
   }
 }
 
-__global__ void hift_source_kernel(const float* __restrict__ f0, const double* __restrict__ D, const float* __restrict__ phase,
-                                   const float* __restrict__ noise, const float* __restrict__ lw, const float* __restrict__ lb,
-                                   const int* __restrict__ len, int B, int Tmax, float* __restrict__ s, int Dld) {
+// Four consecutive samples per thread (480 = 4 * 120: they share a mel frame): the nine noise planes are read and s is
+// written as 16-byte vectors, which is what makes the kernel bandwidth-bound (36 B in + 4 B out per sample).  Unvoiced
+// frames (uv = 0) skip the nine sines: `sine * 0 + noise` is the noise.  Voiced frames evaluate sin with the MUFU after an
+// exact range reduction to [-pi, pi] (|error| < 1e-6 on a 0.1-amplitude term; the phase itself is the fp64 prefix rounded
+// to fp32 exactly as torch's cumsum does).
+__global__ void __launch_bounds__(256) hift_source_kernel(const float* __restrict__ f0, const double* __restrict__ D,
+                                                          const float* __restrict__ phase, const float* __restrict__ noise,
+                                                          const float* __restrict__ lw, const float* __restrict__ lb,
+                                                          const int* __restrict__ len, int B, int Tmax, float* __restrict__ s, int Dld) {
   const long L = 480L * Tmax;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)B * L) return;
+  const long idx4 = (long)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 samples
+  if (idx4 * 4 >= (long)B * L) return;
+  const long idx = idx4 * 4;
   const int b = (int)(idx / L);
-  const long j = idx % L;
-  const int t = (int)(j / 480), jj = (int)(j % 480);
-  if (t >= len[b]) { s[idx] = 0.f; return; }
+  const long j = idx - (long)b * L;
+  const int t = (int)(j / 480), jj = (int)(j - 480L * t);
+  float4* out = reinterpret_cast<float4*>(s + idx);
+  if (t >= len[b]) {
+    *out = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const float f = f0[(long)b * Tmax + t];
-  const float uv = f > 10.0f ? 1.0f : 0.0f;
-  const float noise_amp = f > 10.0f ? 0.003f : (0.1f / 3.0f);
-  float acc = lb[0];
+  const bool voiced = f > 10.0f;
+  const float noise_amp = voiced ? 0.003f : (0.1f / 3.0f);
+  const float bias = lb[0];
+  float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
   for (int h = 0; h < 9; ++h) {
-    const float F = f * (float)(h + 1) / 24000.0f;
-    const double cum = D[((long)b * 9 + h) * Dld + t] + (double)(jj + 1) * (double)F;
-    const float cf = (float)cum;
-    const float frac = cf - floorf(cf);  // fp32 `% 1` of a non-negative value
-    const float theta = 6.283185307179586f * frac;
-    const float ph = h == 0 ? 0.f : phase[b * 9 + h];
-    const float sine = 0.1f * sinf(theta + ph);
-    const float v = sine * uv + noise_amp * noise[((long)b * 9 + h) * L + j];
-    acc = fmaf(lw[h], v, acc);
+    const float4 nz = __ldcs(reinterpret_cast<const float4*>(noise + ((long)b * 9 + h) * L + j));  // streamed: read once
+    const float w = lw[h];
+    float v[4] = {noise_amp * nz.x, noise_amp * nz.y, noise_amp * nz.z, noise_amp * nz.w};
+    if (voiced) {  // warp-uniform except at frame boundaries (120 threads per frame)
+      const float F = f * (float)(h + 1) / 24000.0f;
+      const double d0 = D[((long)b * 9 + h) * Dld + t];
+      const double Fd = (double)F;
+      const float ph = h == 0 ? 0.f : phase[b * 9 + h];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float cf = (float)(d0 + (double)(jj + i + 1) * Fd);
+        const float frac = cf - floorf(cf);  // fp32 `% 1` of a non-negative value
+        float x = 6.283185307179586f * frac + ph;  // in (-pi, 3 pi)
+        if (x > 3.14159265358979f) x -= 6.283185307179586f;
+        v[i] += 0.1f * sin_ftz(x);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = fmaf(w, v[i], acc[i]);
   }
-  s[idx] = tanhf(acc);
+  *out = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
 }
 
 // ---------------------------------------------------------------- STFT of the source (generator.py:371-381)
@@ -118,40 +140,66 @@ struct StftTables {
   float ws[9][16];  // -w[n] * sin(2 pi k n / 16)
 };
 
+// One thread per frame computes its 18 values; the block's 128 x 18 outputs are contiguous in SST, so they leave through
+// shared memory as 16-byte vectors (one thread per frame storing 18 scalars at a 36-byte stride ran at 8 % of HBM peak).
+// The 16 input samples of neighbouring frames overlap by 12: they are read through L1 (__ldg), 4 B per sample from DRAM.
 template <typename TA>
-__global__ void hift_stft_kernel(TA* __restrict__ SST, const int* __restrict__ fr, HiftSeq sq, int rows,
-                                 const float* __restrict__ s, int Tmax, const StftTables tb) {
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= rows) return;
-  const int b = fr[m];
-  TA* o = SST + (long)m * 18;
+__global__ void __launch_bounds__(128) hift_stft_kernel(TA* __restrict__ SST, const int* __restrict__ fr, HiftSeq sq, int rows,
+                                                        const float* __restrict__ s, int Tmax, const StftTables tb) {
+  __shared__ __align__(16) TA tile[128 * 18];
+  __shared__ float s_wc[9][16], s_ws[9][16];
+  for (int i = threadIdx.x; i < 144; i += 128) {
+    s_wc[i >> 4][i & 15] = tb.wc[i >> 4][i & 15];
+    s_ws[i >> 4][i & 15] = tb.ws[i >> 4][i & 15];
+  }
+  __syncthreads();
+  const int m0 = blockIdx.x * 128;
+  const int m = m0 + threadIdx.x;
+  const int b = m < rows ? fr[m] : -1;
+  TA* o = tile + threadIdx.x * 18;
   if (b < 0) {
 #pragma unroll
     for (int k = 0; k < 18; ++k) o[k] = DT<TA>::from_f(0.f);
-    return;
-  }
-  const int f = m - 120 * sq.off[b];
-  const int L = 480 * sq.len[b];
-  const float* sb = s + (long)b * 480 * Tmax;
-  float x[16];
+  } else {
+    const int f = m - 120 * sq.off[b];
+    const int L = 480 * sq.len[b];
+    const float* sb = s + (long)b * 480 * Tmax;
+    float x[16];
+    if (f >= 2 && 4 * f + 8 <= L) {  // interior frame: four aligned 16-byte loads
 #pragma unroll
-  for (int n = 0; n < 16; ++n) {
-    int i = 4 * f - 8 + n;
-    if (i < 0) i = -i;
-    if (i >= L) i = 2 * (L - 1) - i;
-    x[n] = sb[i];
-  }
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(sb + 4 * f - 8) + q);
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+      }
+    } else {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    float re = 0.f, im = 0.f;
-#pragma unroll
-    for (int n = 0; n < 16; ++n) {
-      re = fmaf(x[n], tb.wc[k][n], re);
-      im = fmaf(x[n], tb.ws[k][n], im);
+      for (int n = 0; n < 16; ++n) {
+        int i = 4 * f - 8 + n;
+        if (i < 0) i = -i;
+        if (i >= L) i = 2 * (L - 1) - i;
+        x[n] = sb[i];
+      }
     }
-    o[k] = DT<TA>::from_f(re);
-    o[9 + k] = DT<TA>::from_f(im);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float re = 0.f, im = 0.f;
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        re = fmaf(x[n], s_wc[k][n], re);
+        im = fmaf(x[n], s_ws[k][n], im);
+      }
+      o[k] = DT<TA>::from_f(re);
+      o[9 + k] = DT<TA>::from_f(im);
+    }
   }
+  __syncthreads();
+  const int valid = min(128, rows - m0);
+  constexpr int VEC = 16 / (int)sizeof(TA);  // elements per 16-byte vector
+  const int n_el = valid * 18;
+  TA* dst = SST + (long)m0 * 18;             // 128 * 18 * sizeof(TA) is a multiple of 16: every block starts aligned
+  for (int i = threadIdx.x * VEC; i + VEC <= n_el; i += 128 * VEC)
+    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(tile + i);
+  for (int i = (n_el / VEC) * VEC + threadIdx.x; i < n_el; i += 128) dst[i] = tile[i];
 }
 
 // out[b, k, f] = SST[120 * off_b + f, k] for f < 120 * len_b + 1, else 0  (inspection hook: jv_hift_stft)
@@ -229,14 +277,21 @@ __global__ void mean3_act_kernel(const float* __restrict__ a, const float* __res
 
 // ---------------------------------------------------------------- output head (generator.py:425-431, 383-394)
 // SPEC[m, 0:9] = log-magnitude, SPEC[m, 9:18] = pre-sin phase for frame m.  y[n] = OLA / envelope, clamp.
+constexpr int SPEC_LD = 24;  // conv_post output: 18 channels padded to 24 (the tcgen05 GEMM wants N % 8 == 0; 96-byte rows)
+
 struct IstftTables {
   float cr[9][16];  // c_k cos(2 pi k j / 16) / 16 * w[j]
   float ci[9][16];  // -c_k sin(2 pi k j / 16) / 16 * w[j]  (0 for k = 0, 8)
   float w2[16];
 };
 
+// SPEC rows are `ld` = SPEC_LD floats apart (18 values + padding); the 67 rows a block needs are one
+// contiguous span, staged with 16-byte loads.  exp / sin / sincos run on the MUFU (ex2 / sin / cos .approx after an exact
+// range reduction: relative error ~1e-6, three per bin instead of ~100 FFMA-pipe instructions of libm each -- the kernel
+// was bound by those, not by HBM).
 __global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict__ SPEC, int ld, HiftSeq sq, int Tmax,
-                                                         float* __restrict__ wav, const IstftTables tb, float limit) {
+                                                         float* __restrict__ wav, const IstftTables tb, float limit, long spec_rows) {
+  __shared__ __align__(16) float raw[67 * SPEC_LD];
   __shared__ float re[67][9];
   __shared__ float im[67][9];
   // the synthesis tables are indexed by a per-lane sample phase j: from the constant bank (kernel parameter) that is a
@@ -253,27 +308,42 @@ __global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict
   const int n0 = blockIdx.x * 256;  // first output sample of this block
   const long Lmax = 480L * Tmax;
   if (n0 >= 480 * Tmax) return;
+  const int n = n0 + threadIdx.x;
+  if (n0 >= 480 * T) {  // block entirely beyond the utterance
+    if (n < 480 * Tmax) wav[(long)b * Lmax + n] = 0.f;
+    return;
+  }
   const int F = 120 * T + 1;
   const int f_lo = n0 / 4 + 2 - 3;  // frames f_lo .. f_lo + 66 cover samples n0 .. n0 + 255
   const long row0 = 120L * sq.off[b];
+  {  // rows row0 + f_lo .. + 66, clipped to the buffer: one contiguous span of 16-byte vectors (ld % 4 == 0)
+    const long first = row0 + f_lo;
+    const int vec_per_row = ld >> 2;
+    for (int i = threadIdx.x; i < 67 * vec_per_row; i += 256) {
+      const long rrow = first + i / vec_per_row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rrow >= 0 && rrow < spec_rows) v = __ldcs(reinterpret_cast<const float4*>(SPEC + rrow * ld) + i % vec_per_row);
+      *reinterpret_cast<float4*>(raw + (i / vec_per_row) * SPEC_LD + (i % vec_per_row) * 4) = v;
+    }
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < 67 * 9; i += 256) {
     const int fi = i / 9, k = i % 9;
     const int f = f_lo + fi;
     float r = 0.f, q = 0.f;
     if (f >= 0 && f < F) {
-      const float* sp = SPEC + (row0 + f) * ld;
-      const float mag = fminf(expf(sp[k]), 100.0f);
-      const float ph = sinf(sp[9 + k]);
-      float sn, cs;
-      sincosf(ph, &sn, &cs);
+      const float lm = raw[fi * SPEC_LD + k], px = raw[fi * SPEC_LD + 9 + k];
+      const float mag = fminf(exp_fast(lm), 100.0f);
+      const float ph = sin_ftz(px - 6.283185307179586f * rintf(px * 0.15915494309189535f));  // sin(x), x reduced to [-pi, pi]
+      float cs;
+      asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ph));  // |ph| <= 1
       r = mag * cs;
-      q = mag * sn;
+      q = mag * sin_ftz(ph);
     }
     re[fi][k] = r;
     im[fi][k] = q;
   }
   __syncthreads();
-  const int n = n0 + threadIdx.x;
   if (n >= 480 * Tmax) return;
   float y = 0.f;
   if (n < 480 * T) {

@@ -17,6 +17,7 @@ from . import _lib
 from ._tables import estimator_keys, build_param_tree
 
 DEFAULT_PRECISION = os.environ.get("JYUTVOICE_B200_PRECISION", "bf16")
+_STREAM_FORMATS = {"fp16": 0, "bf16": 1, "fp32": 2}
 
 
 def _lens_from_mask(mask):
@@ -98,7 +99,7 @@ class CausalConditionalDecoder(nn.Module):
             try:
                 _lib.set_weights(h, L.jv_estimator_set_weight, self.state_dict().items())
                 _lib.check(L.jv_estimator_finalize(h))
-                _lib.check(L.jv_estimator_set_stream_format(h, 0 if self.stream_format == "fp16" else 1))
+                _lib.check(L.jv_estimator_set_stream_format(h, _STREAM_FORMATS[self.stream_format]))
             except Exception:
                 L.jv_estimator_destroy(h)
                 raise
@@ -118,25 +119,25 @@ class CausalConditionalDecoder(nn.Module):
         return int(n.value)
 
     def set_stream_format(self, fmt):
-        """"fp16" (default: 11 significand bits, saturating) or "bf16" (fp32 range, 8 bits)."""
-        if fmt not in ("fp16", "bf16"):
-            raise ValueError("stream format must be 'fp16' or 'bf16'")
+        """"fp16" (default: 11 significand bits, saturating), "bf16" (fp32 range, 8 bits) or "fp32"."""
+        if fmt not in _STREAM_FORMATS:
+            raise ValueError(f"stream format must be one of {list(_STREAM_FORMATS)}")
         self.stream_format = fmt
         if self._handle is not None:
-            _lib.check(_lib.lib().jv_estimator_set_stream_format(self._handle, 0 if fmt == "fp16" else 1))
+            _lib.check(_lib.lib().jv_estimator_set_stream_format(self._handle, _STREAM_FORMATS[fmt]))
 
     def _guard_saturation(self):
         """Called before every launch: if an EARLIER call saturated the fp16 stream (weights with outlier activations),
-        say so once and store the stream as bf16 from now on.  Reads a pinned counter: no device synchronisation."""
+        say so once and keep the stream in fp32 from now on (a stream that large has out-grown 16-bit resolution too).  Reads a pinned counter: no device synchronisation."""
         if self.precision != "bf16" or self.stream_format != "fp16" or self._handle is None:
             return
         n = self.saturation_count(synchronize=False)
         if n > self._sat_seen:
             import warnings
             warnings.warn(f"jyutvoice_b200: {n - self._sat_seen} residual-stream rows reached the fp16 range in the previous "
-                          "call; its output may be clipped.  Switching this estimator's stream to bf16.", RuntimeWarning)
+                          "call; its output may be clipped.  Switching this estimator's stream to fp32.", RuntimeWarning)
             self._sat_seen = n
-            self.set_stream_format("bf16")
+            self.set_stream_format("fp32")
 
     @torch.inference_mode()
     def time_embedding(self, t):
