@@ -140,6 +140,39 @@ int jv_hift_stft(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const fl
 int jv_hift_decode(jv_hift* h, int B, int Tmax, const int32_t* lens_host, const float* mel,
                    const float* s, float* wav, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Text front of JyutVoiceTTS.synthesise (jyutvoice/models/jyutvoice_tts.py:175-203), batched over ragged utterances:
+ * TextEncoder (models/text_encoder.py:340-451: embeddings, ConvReluNorm prenet, 6 RoPE attention layers, proj),
+ * DurationPredictor (models/duration_predictor.py:26-60) and the length regulator.  fp32 in both precision modes (the
+ * durations pass through ceil()).  One handle holds the encoder's weights, the predictor's, or both.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct jv_text jv_text;
+int jv_text_create(int device, jv_text** out);
+void jv_text_destroy(jv_text* h);
+/* `key` = "encoder." + TextEncoder.state_dict() key, or "dp." + DurationPredictor.state_dict() key (the names they have
+ * inside JyutVoiceTTS.state_dict()).  Embedding tables may have any number of rows (n_vocab, n_lang, n_tone). */
+int jv_text_set_weight(jv_text* h, const char* key, const float* data, const int64_t* shape, int ndim);
+int jv_text_finalize(jv_text* h);
+size_t jv_text_workspace_bytes(const jv_text* h, int B, int Tx, const int32_t* x_lens_host);
+/* TextEncoder.forward(x, x_lengths, lang, tone, word_pos, syllable_pos, spk_embed) (text_encoder.py:401-451):
+ * token streams dev int64 [B,Tx], spk_embed dev [B,192] -> out_x dev [B,576,Tx], out_mu dev [B,80,Tx]; positions beyond
+ * x_lens[b] are 0 (the reference's `* x_mask`). */
+int jv_text_encode(jv_text* h, int B, int Tx, const int32_t* x_lens_host, const int64_t* x, const int64_t* lang,
+                   const int64_t* tone, const int64_t* word_pos, const int64_t* syllable_pos, const float* spk_embed,
+                   float* out_x, float* out_mu, void* ws, size_t ws_bytes, void* stream);
+/* DurationPredictor.forward(x, x_mask, g) (duration_predictor.py:48-60): x dev [B,576,Tx], spk_embed dev [B,192]
+ * -> out_logw dev [B,1,Tx], 0 beyond x_lens[b]. */
+int jv_text_durations(jv_text* h, int B, int Tx, const int32_t* x_lens_host, const float* x, const float* spk_embed,
+                      float* out_logw, void* ws, size_t ws_bytes, void* stream);
+/* Length regulation (jyutvoice_tts.py:184-203, utils/model.py:29-46), on the current device.  Step 1:
+ * w_ceil = ceil(exp(logw) * mask) * length_scale, cum = cumsum(w_ceil) (dev [B,Tx]), y_lengths = max(sum, 1) truncated
+ * (dev int64 [B]; the caller reads them to size the next call).  Step 2: frame t of utterance b copies the token i with
+ * cum[i-1] <= t < cum[i]: mu_y dev [B,80,Ty] = the gather form of attn^T @ mu_x, frame_token dev int32 [B,Ty] = i or -1. */
+int jv_length_durations(int B, int Tx, const int32_t* x_lens_dev, const float* logw, float length_scale, float* cum,
+                        int64_t* y_lengths, void* stream);
+int jv_length_align(int B, int Tx, int Ty, const int32_t* x_lens_dev, const int64_t* y_lengths, const float* cum,
+                    const float* mu_x, float* mu_y, int32_t* frame_token, void* stream);
+
 /* Profiling of the dominant kernel (the tcgen05 GEMM): between begin and end every launch of it is
  * bracketed by CUDA events on its own stream.  end() synchronises the device and returns the summed
  * kernel time, the summed algorithmic FLOPs (valid frames only) and the launch count. */

@@ -1,6 +1,8 @@
-"""jyutvoice_b200: B200-native (sm_100a) CFM + HiFT hot path behind the reference's Python API."""
+"""jyutvoice_b200: B200-native (sm_100a) text front + CFM + HiFT hot path behind the reference's Python API."""
 from .flow_matching import CausalConditionalCFM, CausalConditionalDecoder  # noqa: F401
 from .hifigan import HiFTGenerator, ConvRNNF0Predictor  # noqa: F401
+from .text import TextEncoder, DurationPredictor, length_regulate  # noqa: F401
 from .tts import JyutVoiceTTS  # noqa: F401
 
-__all__ = ["CausalConditionalCFM", "CausalConditionalDecoder", "HiFTGenerator", "ConvRNNF0Predictor", "JyutVoiceTTS"]
+__all__ = ["CausalConditionalCFM", "CausalConditionalDecoder", "HiFTGenerator", "ConvRNNF0Predictor", "TextEncoder",
+           "DurationPredictor", "length_regulate", "JyutVoiceTTS"]

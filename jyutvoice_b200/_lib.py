@@ -53,6 +53,16 @@ SIGNATURES = {
     "jv_hift_f0": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "jv_hift_source": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "jv_hift_decode": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "jv_text_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    "jv_text_destroy": (None, [c_void_p]),
+    "jv_text_set_weight": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, P_i64, c_int]),
+    "jv_text_finalize": (c_int, [c_void_p]),
+    "jv_text_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, P_i32]),
+    "jv_text_encode": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "jv_text_durations": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "jv_length_durations": (c_int, [c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+    "jv_length_align": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "jv_profile_begin": (c_int, []),
     "jv_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "jv_bench_gemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_double)]),

@@ -109,6 +109,61 @@ def hift_table():
 
 
 
+def text_encoder_table(n_vocab=97, n_lang=4, n_tone=7, prefix=""):
+    """TextEncoder.state_dict() (jyutvoice/models/text_encoder.py:340-420) with the base.yaml encoder_params:
+    n_channels 192, gin_channels 192 -> hidden 576, filter 768, 2 heads, 6 layers, kernel 3, prenet (3 x conv k5).
+    kind adds: emb (embedding table, N(0, C^-0.5))."""
+    t = []
+    C, H, Fc = 192, 576, 768
+    for name, n in (("emb", n_vocab), ("lang_emb", n_lang), ("tone_emb", n_tone), ("word_pos_emb", 4), ("syllable_pos", 4)):
+        t.append((f"{name}.weight", (n, C), "emb"))
+    for i in range(3):
+        t.append((f"prenet.conv_layers.{i}.weight", (C, C, 5), "w"))
+        t.append((f"prenet.conv_layers.{i}.bias", (C,), "b"))
+    for i in range(3):
+        t.append((f"prenet.norm_layers.{i}.gamma", (C,), "g"))
+        t.append((f"prenet.norm_layers.{i}.beta", (C,), "beta"))
+    t.append(("prenet.proj.weight", (C, C, 1), "w"))
+    t.append(("prenet.proj.bias", (C,), "b"))
+    for i in range(6):
+        for c in ("q", "k", "v", "o"):
+            t.append((f"encoder.attn_layers.{i}.conv_{c}.weight", (H, H, 1), "w"))
+            t.append((f"encoder.attn_layers.{i}.conv_{c}.bias", (H,), "b"))
+    for i in range(6):
+        t.append((f"encoder.norm_layers_1.{i}.gamma", (H,), "g"))
+        t.append((f"encoder.norm_layers_1.{i}.beta", (H,), "beta"))
+    for i in range(6):
+        t.append((f"encoder.ffn_layers.{i}.conv_1.weight", (Fc, H, 3), "w"))
+        t.append((f"encoder.ffn_layers.{i}.conv_1.bias", (Fc,), "b"))
+        t.append((f"encoder.ffn_layers.{i}.conv_2.weight", (H, Fc, 3), "w"))
+        t.append((f"encoder.ffn_layers.{i}.conv_2.bias", (H,), "b"))
+    for i in range(6):
+        t.append((f"encoder.norm_layers_2.{i}.gamma", (H,), "g"))
+        t.append((f"encoder.norm_layers_2.{i}.beta", (H,), "beta"))
+    t.append(("proj.weight", (80, H, 1), "w"))
+    t.append(("proj.bias", (80,), "b"))
+    return [(prefix + k, s_, kind) for k, s_, kind in t]
+
+
+def duration_predictor_table(prefix=""):
+    """DurationPredictor.state_dict() (jyutvoice/models/duration_predictor.py:26-46): in 576, filter 256, kernel 3, gin 192."""
+    t = [("conv_1.weight", (256, 576, 3), "w"), ("conv_1.bias", (256,), "b"),
+         ("norm_1.gamma", (256,), "g"), ("norm_1.beta", (256,), "beta"),
+         ("conv_2.weight", (256, 256, 3), "w"), ("conv_2.bias", (256,), "b"),
+         ("norm_2.gamma", (256,), "g"), ("norm_2.beta", (256,), "beta"),
+         ("proj.weight", (1, 256, 1), "w"), ("proj.bias", (1,), "b"),
+         ("cond.weight", (576, 192, 1), "w"), ("cond.bias", (576,), "b")]
+    return [(prefix + k, s_, kind) for k, s_, kind in t]
+
+
+def text_encoder_keys(n_vocab=97, n_lang=4, n_tone=7):
+    return [(k, tuple(s_)) for k, s_, _ in text_encoder_table(n_vocab, n_lang, n_tone)]
+
+
+def duration_predictor_keys():
+    return [(k, tuple(s_)) for k, s_, _ in duration_predictor_table()]
+
+
 def _bias_shape(table, idx):
     # bias of a weight-normed conv: out channels.  ConvTranspose (ups.*) has Cout = shape[1].
     key = table[idx][0]

@@ -327,13 +327,13 @@ static void run_resnet(const FwdCtx& c, const ResnetW& w, int layer, const void*
   e.gemm(g, c.st);
 }
 
-// JYUTVOICE_B200_MLP=1 opts in to the fused feed-forward kernel (mlp_tc.cuh); the default is the two-launch
-// feed-forward (FF1 + GELU, FF2 + residual + norm), which is faster today
+// The fused feed-forward kernel (mlp_tc.cuh, CTA-pair variant) is the default with the fp16 stream;
+// JYUTVOICE_B200_MLP=0 selects the two-launch feed-forward (FF1 + GELU, FF2 + residual + norm)
 static bool use_mlp_fused() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("JYUTVOICE_B200_MLP");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
@@ -358,7 +358,7 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
     const bool to_copy = copy_to != nullptr;
     launch_mlp_fused(e.tmaps, c.b.LNX, w.ff1.W, w.ff1.bias, w.ff2.W, w.ff2.bias, c.b.X, to_copy ? copy_to : c.b.X, to_copy ? 0 : 1,
                      next_ln ? next_ln->g : nullptr, next_ln ? next_ln->b : nullptr, next_ln ? c.b.LNX : nullptr, c.b.frame_row,
-                     c.M_alloc, e.num_sms, 2.0 * (double)c.valid_frames * (2.0 * C * 1024), c.st);
+                     c.M_alloc, e.num_sms, 2.0 * (double)c.valid_frames * (2.0 * C * 1024), e.sat_flag, c.st);
     return;
   }
   g = conv_desc(c, w.ff1, c.b.LNX, nullptr, 1);

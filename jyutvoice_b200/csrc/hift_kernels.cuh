@@ -133,6 +133,15 @@ __global__ void __launch_bounds__(256) hift_source_kernel(const float* __restric
   *out = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
 }
 
+// cos(2 pi m / 16): with fully unrolled loops every use below is a compile-time constant, i.e. an FFMA immediate.
+__device__ constexpr float COS16[16] = {1.0f, 0.9238795325112867f, 0.7071067811865476f, 0.3826834323650898f, 0.0f,
+                                        -0.3826834323650898f, -0.7071067811865476f, -0.9238795325112867f, -1.0f,
+                                        -0.9238795325112867f, -0.7071067811865476f, -0.3826834323650898f, 0.0f,
+                                        0.3826834323650898f, 0.7071067811865476f, 0.9238795325112867f};
+#define JV_COS16(m) (COS16[(m) & 15])
+#define JV_SIN16(m) (COS16[((m) + 12) & 15])          /* sin x = cos(x - pi / 2) */
+#define JV_HANN16(n) (0.5f - 0.5f * COS16[(n) & 15])  /* periodic hann window of 16 */
+
 // ---------------------------------------------------------------- STFT of the source (generator.py:371-381)
 // 16-point DFT, hop 4, periodic hann, center + reflect padding (per utterance at its own length).
 struct StftTables {
@@ -147,12 +156,8 @@ template <typename TA>
 __global__ void __launch_bounds__(128) hift_stft_kernel(TA* __restrict__ SST, const int* __restrict__ fr, HiftSeq sq, int rows,
                                                         const float* __restrict__ s, int Tmax, const StftTables tb) {
   __shared__ __align__(16) TA tile[128 * 18];
-  __shared__ float s_wc[9][16], s_ws[9][16];
-  for (int i = threadIdx.x; i < 144; i += 128) {
-    s_wc[i >> 4][i & 15] = tb.wc[i >> 4][i & 15];
-    s_ws[i >> 4][i & 15] = tb.ws[i >> 4][i & 15];
-  }
-  __syncthreads();
+  // The analysis tables stay in the kernel-parameter constant bank: after full unrolling every tb.wc[k][n] is a compile-time
+  // address, i.e. an FFMA operand.  (A shared-memory copy costs one LDS per FFMA: 288 per frame bound the kernel at 83 us.)
   const int m0 = blockIdx.x * 128;
   const int m = m0 + threadIdx.x;
   const int b = m < rows ? fr[m] : -1;
@@ -180,16 +185,46 @@ __global__ void __launch_bounds__(128) hift_stft_kernel(TA* __restrict__ SST, co
         x[n] = sb[i];
       }
     }
+    // 16-point real DFT of the windowed frame with the n <-> 16 - n and k <-> 8 - k symmetries folded in (~120 FMAs
+    // with immediate twiddles instead of 288 table FMAs: the kernel was bound by those, not by HBM)
+    float xw[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) xw[n] = x[n] * JV_HANN16(n);
+    float a[9], bb[8];  // a_n = xw_n + xw_{16-n}, b_n = xw_n - xw_{16-n}
+    a[0] = xw[0];
+    a[8] = xw[8];
+#pragma unroll
+    for (int n = 1; n < 8; ++n) {
+      a[n] = xw[n] + xw[16 - n];
+      bb[n] = xw[n] - xw[16 - n];
+    }
+    float re[9], im[9];
+#pragma unroll
+    for (int k = 0; k <= 4; ++k) {  // Re_k = E + O, Re_{8-k} = E - O (E: even n, O: odd n)
+      float E = 0.f, O = 0.f;
+#pragma unroll
+      for (int n = 0; n <= 8; n += 2) E = fmaf(a[n], JV_COS16(k * n), E);
+#pragma unroll
+      for (int n = 1; n < 8; n += 2) O = fmaf(a[n], JV_COS16(k * n), O);
+      re[k] = E + O;
+      re[8 - k] = E - O;
+    }
+    im[0] = 0.f;
+    im[8] = 0.f;
+#pragma unroll
+    for (int k = 1; k <= 4; ++k) {  // Im_k = -(SE + SO), Im_{8-k} = -(SO - SE)
+      float SE = 0.f, SO = 0.f;
+#pragma unroll
+      for (int n = 2; n < 8; n += 2) SE = fmaf(bb[n], JV_SIN16(k * n), SE);
+#pragma unroll
+      for (int n = 1; n < 8; n += 2) SO = fmaf(bb[n], JV_SIN16(k * n), SO);
+      im[k] = -(SE + SO);
+      im[8 - k] = SE - SO;
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      float re = 0.f, im = 0.f;
-#pragma unroll
-      for (int n = 0; n < 16; ++n) {
-        re = fmaf(x[n], s_wc[k][n], re);
-        im = fmaf(x[n], s_ws[k][n], im);
-      }
-      o[k] = DT<TA>::from_f(re);
-      o[9 + k] = DT<TA>::from_f(im);
+      o[k] = DT<TA>::from_f(re[k]);
+      o[9 + k] = DT<TA>::from_f(im[k]);
     }
   }
   __syncthreads();
@@ -285,86 +320,122 @@ struct IstftTables {
   float w2[16];
 };
 
-// SPEC rows are `ld` = SPEC_LD floats apart (18 values + padding); the 67 rows a block needs are one
-// contiguous span, staged with 16-byte loads.  exp / sin / sincos run on the MUFU (ex2 / sin / cos .approx after an exact
-// range reduction: relative error ~1e-6, three per bin instead of ~100 FFMA-pipe instructions of libm each -- the kernel
-// was bound by those, not by HBM).
+// One block = 1024 output samples of one utterance = 256 hops (+ 3 frames of overlap).  Phase 1, one thread per frame:
+// read the frame's 18 values (rows are `ld` = SPEC_LD floats apart: 16-byte loads), magnitude / phase with three MUFU ops
+// per bin (ex2, sin, cos .approx after an exact range reduction; libm's expf / sinf / sincosf bound the old kernel), then the
+// windowed 16-point inverse DFT as FFMAs whose table operands come straight from the constant bank, and the 16 samples
+// go to shared memory.  Phase 2, four samples per thread: overlap-add of the four frames that cover a sample, envelope,
+// clamp, one 16-byte store.
 __global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict__ SPEC, int ld, HiftSeq sq, int Tmax,
                                                          float* __restrict__ wav, const IstftTables tb, float limit, long spec_rows) {
-  __shared__ __align__(16) float raw[67 * SPEC_LD];
-  __shared__ float re[67][9];
-  __shared__ float im[67][9];
-  // the synthesis tables are indexed by a per-lane sample phase j: from the constant bank (kernel parameter) that is a
-  // 16-way serialised access, from shared memory it is conflict-free
-  __shared__ float s_cr[9][16], s_ci[9][16], s_w2[16];
-  if (threadIdx.x < 144) {
-    s_cr[threadIdx.x >> 4][threadIdx.x & 15] = tb.cr[threadIdx.x >> 4][threadIdx.x & 15];
-    s_ci[threadIdx.x >> 4][threadIdx.x & 15] = tb.ci[threadIdx.x >> 4][threadIdx.x & 15];
-  } else if (threadIdx.x < 160) {
-    s_w2[threadIdx.x - 144] = tb.w2[threadIdx.x - 144];
-  }
+  constexpr int NF = 259;             // frames a block touches: f_lo .. f_lo + 258
+  __shared__ float Y[16][NF + 1];     // Y[j][frame]: sample j of the frame's windowed inverse DFT (conflict-free in both phases)
   const int b = blockIdx.y;
   const int T = sq.len[b];
-  const int n0 = blockIdx.x * 256;  // first output sample of this block
+  const int n0 = blockIdx.x * 1024;   // first output sample of this block
   const long Lmax = 480L * Tmax;
   if (n0 >= 480 * Tmax) return;
-  const int n = n0 + threadIdx.x;
+  float4* out = reinterpret_cast<float4*>(wav + (long)b * Lmax + n0) + threadIdx.x;
+  const int n = n0 + 4 * threadIdx.x;
   if (n0 >= 480 * T) {  // block entirely beyond the utterance
-    if (n < 480 * Tmax) wav[(long)b * Lmax + n] = 0.f;
+    if (n < 480 * Tmax) *out = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
   const int F = 120 * T + 1;
-  const int f_lo = n0 / 4 + 2 - 3;  // frames f_lo .. f_lo + 66 cover samples n0 .. n0 + 255
+  const int f_lo = n0 / 4 - 1;        // sample n is covered by frames (n + 8) / 4 - 3 .. (n + 8) / 4
   const long row0 = 120L * sq.off[b];
-  {  // rows row0 + f_lo .. + 66, clipped to the buffer: one contiguous span of 16-byte vectors (ld % 4 == 0)
-    const long first = row0 + f_lo;
-    const int vec_per_row = ld >> 2;
-    for (int i = threadIdx.x; i < 67 * vec_per_row; i += 256) {
-      const long rrow = first + i / vec_per_row;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rrow >= 0 && rrow < spec_rows) v = __ldcs(reinterpret_cast<const float4*>(SPEC + rrow * ld) + i % vec_per_row);
-      *reinterpret_cast<float4*>(raw + (i / vec_per_row) * SPEC_LD + (i % vec_per_row) * 4) = v;
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 67 * 9; i += 256) {
-    const int fi = i / 9, k = i % 9;
+  for (int fi = threadIdx.x; fi < NF; fi += 256) {
     const int f = f_lo + fi;
-    float r = 0.f, q = 0.f;
-    if (f >= 0 && f < F) {
-      const float lm = raw[fi * SPEC_LD + k], px = raw[fi * SPEC_LD + 9 + k];
-      const float mag = fminf(exp_fast(lm), 100.0f);
-      const float ph = sin_ftz(px - 6.283185307179586f * rintf(px * 0.15915494309189535f));  // sin(x), x reduced to [-pi, pi]
-      float cs;
-      asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ph));  // |ph| <= 1
-      r = mag * cs;
-      q = mag * sin_ftz(ph);
+    float y[16];
+    if (f >= 0 && f < F && row0 + f < spec_rows) {
+      const float4* sp = reinterpret_cast<const float4*>(SPEC + (row0 + f) * ld);
+      float v[20];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float4 t = __ldcs(sp + q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      }
+      float re[9], im[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float mag = fminf(exp_fast(v[k]), 100.0f);
+        const float px = v[9 + k];
+        const float ph = sin_ftz(px - 6.283185307179586f * rintf(px * 0.15915494309189535f));  // sin(x), x reduced to [-pi, pi]
+        float cs;
+        asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ph));  // |ph| <= 1
+        re[k] = mag * cs;
+        im[k] = mag * sin_ftz(ph);
+      }
+      // windowed inverse real DFT, y[j] = w[j] / 16 * sum_k c_k (Re_k cos(2 pi k j / 16) - Im_k sin(2 pi k j / 16)), c = 1 for
+      // k in {0, 8} else 2, with the j <-> 16 - j and j <-> 8 - j symmetries folded in (immediate twiddles, ~115 FMAs)
+      float cre[9], cim[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float c = (k == 0 || k == 8) ? 1.0f : 2.0f;
+        cre[k] = c * re[k];
+        cim[k] = c * im[k];
+      }
+      float A[9], Bs[9];  // A symmetric, Bs antisymmetric in j <-> 16 - j
+#pragma unroll
+      for (int j = 0; j <= 4; ++j) {  // A[j] = AE + AO, A[8 - j] = AE - AO (even / odd k)
+        float AE = 0.f, AO = 0.f;
+#pragma unroll
+        for (int k = 0; k <= 8; k += 2) AE = fmaf(cre[k], JV_COS16(k * j), AE);
+#pragma unroll
+        for (int k = 1; k < 8; k += 2) AO = fmaf(cre[k], JV_COS16(k * j), AO);
+        A[j] = AE + AO;
+        A[8 - j] = AE - AO;
+      }
+      Bs[0] = 0.f;
+      Bs[8] = 0.f;
+#pragma unroll
+      for (int j = 1; j <= 4; ++j) {  // Bs[j] = BE + BO, Bs[8 - j] = BO - BE
+        float BE = 0.f, BO = 0.f;
+#pragma unroll
+        for (int k = 2; k < 8; k += 2) BE = fmaf(cim[k], JV_SIN16(k * j), BE);
+#pragma unroll
+        for (int k = 1; k < 8; k += 2) BO = fmaf(cim[k], JV_SIN16(k * j), BO);
+        Bs[j] = BE + BO;
+        Bs[8 - j] = BO - BE;
+      }
+      y[0] = (JV_HANN16(0) * 0.0625f) * A[0];
+      y[8] = (JV_HANN16(8) * 0.0625f) * A[8];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) {
+        y[j] = (JV_HANN16(j) * 0.0625f) * (A[j] - Bs[j]);
+        y[16 - j] = (JV_HANN16(16 - j) * 0.0625f) * (A[j] + Bs[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = 0.f;
     }
-    re[fi][k] = r;
-    im[fi][k] = q;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) Y[j][fi] = y[j];
   }
   __syncthreads();
   if (n >= 480 * Tmax) return;
-  float y = 0.f;
-  if (n < 480 * T) {
-    const int f_hi = (n + 8) / 4;
-    float acc = 0.f, env = 0.f;
+  float r[4];
 #pragma unroll
-    for (int d = 3; d >= 0; --d) {
-      const int f = f_hi - d;
-      if (f < 0 || f >= F) continue;
-      const int j = n + 8 - 4 * f;
-      const int fi = f - f_lo;
-      float v = 0.f;
+  for (int i = 0; i < 4; ++i) {
+    const int ni = n + i;
+    float yv = 0.f;
+    if (ni < 480 * T) {
+      const int f_hi = (ni + 8) / 4;
+      float acc = 0.f, env = 0.f;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) v = fmaf(re[fi][k], s_cr[k][j], fmaf(im[fi][k], s_ci[k][j], v));
-      acc += v;
-      env += s_w2[j];
+      for (int d = 3; d >= 0; --d) {
+        const int f = f_hi - d;
+        if (f < 0 || f >= F) continue;
+        const int j = ni + 8 - 4 * f;  // = 4 d + i: compile-time after unrolling
+        acc += Y[j][f - f_lo];
+        env += JV_HANN16(j) * JV_HANN16(j);
+      }
+      yv = acc / env;
+      yv = fminf(fmaxf(yv, -limit), limit);
     }
-    y = acc / env;
-    y = fminf(fmaxf(y, -limit), limit);
+    r[i] = yv;
   }
-  wav[(long)b * Lmax + n] = y;
+  *out = make_float4(r[0], r[1], r[2], r[3]);
 }
 
 }  // namespace jv

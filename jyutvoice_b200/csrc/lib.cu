@@ -3,3 +3,4 @@
 #include "gemm_tc.cu"
 #include "estimator.cu"
 #include "hift.cu"
+#include "text.cu"

@@ -26,7 +26,7 @@ constexpr int SMEM_BYTES = 1024 + OFF_BAR + 512;
 constexpr int THREADS = 384;
 
 struct Maps {
-  CUtensorMap a, w1, w2;  // bf16 operands, box 64 x 128, SWIZZLE_128B
+  CUtensorMap a, w1, w2;  // bf16 operands, box 64 x 128, SWIZZLE_128B (pair kernel: w1 box 64 x 64, this CTA's half of a chunk)
   CUtensorMap r, o, l;    // 16-bit [rows, 256], box 32 x 32, SWIZZLE_64B: residual in, stream out, LayerNorm out
 };
 struct Params {
@@ -34,6 +34,7 @@ struct Params {
   const float *b1, *b2, *gamma, *beta;  // gamma == nullptr: no LayerNorm output
   const int* frame_row;
   int out_half;  // stream out is fp16 (else bf16: the copy that feeds the next conv)
+  int* sat_flag; // fp16 stream: counts stores that reached +-65504 (see GemmDesc::sat_flag)
 };
 
 __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_constant__ Maps tm, const Params p) {
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         tma_load_2d(&tm.r, ebar + 8, sStage + EPI_B16_BYTES, (sub + 2) * 32, row0);
       }
       const uint32_t taddr = tmem_base + lane_addr + 256;
-      float sum2 = 0.f, sq2 = 0.f;
+      float sum2 = 0.f, sq2 = 0.f, amax = 0.f;
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
         const int cc = sub + 2 * i, n = cc * 32, ib = i & 1;
@@ -294,6 +295,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
         __syncwarp();
         if (p.out_half) {
 #pragma unroll
+          for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+#pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128u(hbuf + swz64(lane, j), pack_f16_sat(v[8 * j], v[8 * j + 1]), pack_f16_sat(v[8 * j + 2], v[8 * j + 3]),
                     pack_f16_sat(v[8 * j + 4], v[8 * j + 5]), pack_f16_sat(v[8 * j + 6], v[8 * j + 7]));
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
           bulk_commit();
         }
       }
+      if (p.out_half && p.sat_flag && amax >= 65504.f) atomicAdd(p.sat_flag, 1);
       if (p.gamma) {
         row_sum2(sum2, sq2);
         const float mean2 = sum2 * (1.0f / C);
@@ -351,21 +355,377 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster share every weight unit -- each fetches HALF of it (64 of the 128
+// W1 rows of a hidden chunk, 128 of the 256 W2 rows) and one M = 256 MMA covers both CTAs' 128-row tiles.  An SM then
+// ingests 0.5 MB of weights per tile instead of 1 MB: the single-CTA kernel was bound by exactly that stream (1 MB per
+// tile through L2 -> SM at ~45 B / clk is 23k clk against 16k clk of MMA time).  Everything else (LNX tile, H buffers,
+// accumulators, epilogues) is per CTA as above.  Ring slot = 16 KB: GEMM1 packs two 64-row K blocks into one slot.
+constexpr int PAIR_SMEM_BYTES = SMEM_BYTES;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fused_pair_kernel(const __grid_constant__ Maps tm, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sA = base + OFF_A, sW = base + OFF_W, sH = base + OFF_H;
+  float* vec = reinterpret_cast<float*>(smem_raw + (base + OFF_VEC - raw));
+  float* xch_all = reinterpret_cast<float*>(smem_raw + (base + OFF_XCH - raw));
+  const uint32_t bars = base + OFF_BAR;
+  const uint32_t a_full = bars, a_empty = bars + 8;
+  const uint32_t w_full = bars + 16, w_empty = w_full + 8 * RW;
+  const uint32_t acc1_full = w_empty + 8 * RW, acc1_empty = acc1_full + 16;
+  const uint32_t h_full = acc1_empty + 16, h_empty = h_full + 16;
+  const uint32_t acc2_full = h_empty + 16, acc2_empty = acc2_full + 8;
+  const uint32_t epi_bar = acc2_empty + 8;  // 8 warps x 2 residual-load barriers
+  const uint32_t tmem_slot = epi_bar + 16 * 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_cta_rank();
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.w2) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    // barriers the LEADER's MMA thread waits on collect both CTAs (16 epilogue warps, both CTAs' TMA bytes);
+    // barriers the MMA thread signals are multicast commits: one arrival in each CTA
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < RW; ++i) {
+      mbar_init(w_full + 8 * i, 1);
+      mbar_init(w_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc1_full + 8 * i, 1);
+      mbar_init(acc1_empty + 8 * i, 16);
+      mbar_init(h_full + 8 * i, 16);
+      mbar_init(h_empty + 8 * i, 1);
+    }
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 16);
+    for (int i = 0; i < 16; ++i) mbar_init(epi_bar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < HID + 3 * C; i += blockDim.x) {  // weights only: safe before pdl_wait
+    float v;
+    if (i < HID) v = p.b1[i];
+    else if (i < HID + C) v = p.b2[i - HID];
+    else if (i < HID + 2 * C) v = p.gamma ? p.gamma[i - HID - C] : 1.f;
+    else v = p.gamma ? p.beta[i - HID - 2 * C] : 0.f;
+    vec[i] = v;
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+  const int num_pairs = (p.num_tiles + 1) >> 1;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      if (lane == 0) {
+        const uint32_t a_full_l = mapa_u32(a_full, 0), w_full_l = mapa_u32(w_full, 0);
+        uint32_t wi = 0, t_local = 0;
+        auto slot_begin = [&]() {
+          const uint32_t slot = wi % RW, ph = (wi / RW) & 1;
+          mbar_wait(w_empty + 8 * slot, ph ^ 1, 31);
+          if (rank == 0) mbar_expect_tx(w_full + 8 * slot, 2 * UNIT);  // both CTAs' 16 KB
+          return slot;
+        };
+        auto load_g1 = [&](int c) {  // W1 rows of hidden chunk c, this CTA's 64: K blocks (0,1) and (2,3) -> two slots
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const uint32_t slot = slot_begin();
+            for (int kb = 0; kb < 2; ++kb)
+              tma_load_2d_cg2(&tm.w1, w_full_l + 8 * slot, sW + slot * UNIT + kb * (UNIT / 2), (2 * s2 + kb) * 64, c * NC + rank * 64);
+            ++wi;
+          }
+        };
+        auto load_g2 = [&](int c) {  // W2 columns of hidden chunk c (two K blocks), this CTA's 128 output rows
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            const uint32_t slot = slot_begin();
+            tma_load_2d_cg2(&tm.w2, w_full_l + 8 * slot, sW + slot * UNIT, c * NC + kb2 * 64, rank * 128);
+            ++wi;
+          }
+        };
+        for (int pt = pair0; pt < num_pairs; pt += pair_step, ++t_local) {
+          const int tile = 2 * pt + rank;
+          mbar_wait(a_empty, (t_local & 1) ^ 1, 32);
+          if (rank == 0) mbar_expect_tx(a_full, 2 * 4 * UNIT);
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d_cg2(&tm.a, a_full_l, sA + kb * UNIT, kb * 64, tile * BLOCK_M);
+          load_g1(0);
+          load_g1(1);
+          for (int c = 0; c < NCH; ++c) {
+            load_g2(c);
+            if (c + 2 < NCH) load_g1(c + 2);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      if (lane == 0 && rank == 0) {
+        const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M 256, N 128
+        const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M 256, N 256
+        uint32_t wi = 0, t_local = 0;
+        uint32_t u1[2] = {0, 0};  // uses of acc1[b] / H[b]
+        uint32_t uh[2] = {0, 0};
+        auto g1 = [&](int c) {
+          const int b = c & 1;
+          mbar_wait(acc1_empty + 8 * b, (u1[b] & 1) ^ 1, 33);
+          tc_fence_after();
+          for (int s2 = 0; s2 < 2; ++s2, ++wi) {
+            const uint32_t slot = wi % RW;
+            mbar_wait(w_full + 8 * slot, (wi / RW) & 1, 34);
+            tc_fence_after();
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint64_t ad = make_smem_desc(sA + (2 * s2 + kb) * UNIT), bd = make_smem_desc(sW + slot * UNIT + kb * (UNIT / 2));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16_cg2(tmem_base + b * NC, ad + 2 * k, bd + 2 * k, idesc1, (s2 | kb | k) ? 1u : 0u);
+            }
+            umma_commit_cg2(w_empty + 8 * slot, 3);
+          }
+          umma_commit_cg2(acc1_full + 8 * b, 3);
+          ++u1[b];
+        };
+        auto g2 = [&](int c) {
+          const int b = c & 1;
+          mbar_wait(h_full + 8 * b, uh[b] & 1, 35);
+          if (c == 0) mbar_wait(acc2_empty, (t_local & 1) ^ 1, 36);
+          tc_fence_after();
+          for (int kb2 = 0; kb2 < 2; ++kb2, ++wi) {
+            const uint32_t slot = wi % RW;
+            mbar_wait(w_full + 8 * slot, (wi / RW) & 1, 37);
+            tc_fence_after();
+            const uint64_t ad = make_smem_desc(sH + b * 2 * UNIT + kb2 * UNIT), bd = make_smem_desc(sW + slot * UNIT);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_cg2(tmem_base + 256, ad + 2 * k, bd + 2 * k, idesc2, (c | kb2 | k) ? 1u : 0u);
+            umma_commit_cg2(w_empty + 8 * slot, 3);
+          }
+          umma_commit_cg2(h_empty + 8 * b, 3);
+          ++uh[b];
+        };
+        for (int pt = pair0; pt < num_pairs; pt += pair_step, ++t_local) {
+          mbar_wait(a_full, t_local & 1, 38);
+          tc_fence_after();
+          g1(0);
+          g1(1);
+          for (int c = 0; c < NCH; ++c) {
+            g2(c);
+            if (c + 2 < NCH) g1(c + 2);
+            if (c + 2 == NCH - 1) umma_commit_cg2(a_empty, 3);  // the pair's last read of LNX has been issued
+          }
+          umma_commit_cg2(acc2_full, 3);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // ===================== epilogue warps (both CTAs, each on its own 128 rows) =====================
+    const int e = warp - 4, q = e & 3, sub = e >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t acc1_empty_l = mapa_u32(acc1_empty, 0), h_full_l = mapa_u32(h_full, 0), acc2_empty_l = mapa_u32(acc2_empty, 0);
+    float* xch = xch_all + q * (2 * 32 * 2);
+    auto row_sum2 = [&](float& a, float& b) {  // summed over the two threads that share a row
+      xch[(sub * 32 + lane) * 2] = a;
+      xch[(sub * 32 + lane) * 2 + 1] = b;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(64) : "memory");
+      const float ta = xch[lane * 2] + xch[(32 + lane) * 2];
+      const float tb = xch[lane * 2 + 1] + xch[(32 + lane) * 2 + 1];
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(64) : "memory");
+      a = ta;
+      b = tb;
+    };
+    const float *v_b1 = vec, *v_b2 = vec + HID, *v_g = vec + HID + C, *v_be = vec + HID + 2 * C;
+    const uint32_t sStage = sH + e * 8192;
+    const uint32_t ebar = epi_bar + 16 * e;
+    uint32_t ephase = 0, n_out = 0;
+    uint32_t u1[2] = {0, 0};
+    uint32_t t_local = 0;
+    for (int pt = pair0; pt < num_pairs; pt += pair_step, ++t_local) {
+      const int tile = 2 * pt + rank;
+      const int m0 = tile * BLOCK_M, row0 = m0 + q * 32;
+      const int m = row0 + lane;
+      const bool row_valid = m < p.M && p.frame_row[m] >= 0;
+      for (int c = 0; c < NCH; ++c) {
+        const int b = c & 1;
+        mbar_wait(acc1_full + 8 * b, u1[b] & 1, 41);
+        tc_fence_after();
+        mbar_wait(h_empty + 8 * b, (u1[b] & 1) ^ 1, 42);
+        ++u1[b];
+        uint32_t a0[32], a1[32];
+        tmem_ld32(tmem_base + lane_addr + b * NC + sub * 64, a0);
+        tmem_ld32(tmem_base + lane_addr + b * NC + sub * 64 + 32, a1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc1_empty_l + 8 * b);
+        const float* bb = v_b1 + c * NC + sub * 64;
+        const uint32_t hk = sH + b * 2 * UNIT + sub * UNIT;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(half ? a1[j] : a0[j]) + bb[half * 32 + j];
+          act32(v, ACT_GELU, 0.f, nullptr, 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128u(hk + swz128(row, half * 4 + j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(h_full_l + 8 * b);
+      }
+      mbar_wait(acc2_full, t_local & 1, 43);
+      tc_fence_after();
+      if (lane == 0) {
+        mbar_expect_tx(ebar, EPI_B16_BYTES);
+        tma_load_2d(&tm.r, ebar, sStage, sub * 32, row0);
+        mbar_expect_tx(ebar + 8, EPI_B16_BYTES);
+        tma_load_2d(&tm.r, ebar + 8, sStage + EPI_B16_BYTES, (sub + 2) * 32, row0);
+      }
+      const uint32_t taddr = tmem_base + lane_addr + 256;
+      float sum2 = 0.f, sq2 = 0.f, amax = 0.f;
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int cc = sub + 2 * i, n = cc * 32, ib = i & 1;
+        uint32_t acc[32];
+        tmem_ld32(taddr + n, acc);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = row_valid ? __uint_as_float(acc[j]) + v_b2[n + j] : 0.f;
+        mbar_wait(ebar + 8 * ib, (ephase >> ib) & 1, 44);
+        ephase ^= 1u << ib;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 r = lds128(sStage + ib * EPI_B16_BYTES + swz64(lane, j));
+          const uint32_t w[4] = {__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z), __float_as_uint(r.w)};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+            v[8 * j + 2 * k] += f.x;
+            v[8 * j + 2 * k + 1] += f.y;
+          }
+        }
+        __syncwarp();
+        if (lane == 0 && i + 2 < 4) {
+          mbar_expect_tx(ebar + 8 * ib, EPI_B16_BYTES);
+          tma_load_2d(&tm.r, ebar + 8 * ib, sStage + ib * EPI_B16_BYTES, (cc + 4) * 32, row0);
+        }
+        if (p.gamma) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            acc[j] = __float_as_uint(v[j]);
+            sum2 += v[j];
+            sq2 = fmaf(v[j], v[j], sq2);
+          }
+          tmem_st32(taddr + n, acc);
+        }
+        const uint32_t hbuf = sStage + (2 + (n_out & 1)) * EPI_B16_BYTES;
+        ++n_out;
+        if (lane == 0) bulk_wait_read1();
+        __syncwarp();
+        if (p.out_half) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128u(hbuf + swz64(lane, j), pack_f16_sat(v[8 * j], v[8 * j + 1]), pack_f16_sat(v[8 * j + 2], v[8 * j + 3]),
+                    pack_f16_sat(v[8 * j + 4], v[8 * j + 5]), pack_f16_sat(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128u(hbuf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm.o, hbuf, n, row0);
+          bulk_commit();
+        }
+      }
+      if (p.out_half && p.sat_flag && amax >= 65504.f) atomicAdd(p.sat_flag, 1);
+      if (p.gamma) {
+        row_sum2(sum2, sq2);
+        const float mean2 = sum2 * (1.0f / C);
+        const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / C) - mean2 * mean2, 0.f) + 1e-5f);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int n = (sub + 2 * i) * 32;
+          uint32_t acc[32];
+          tmem_ld32(taddr + n, acc);
+          float v[32];
+          acc_to_f32(acc, v);
+          ln_affine32(v, mean2, rstd2, v_g + n, v_be + n);
+          if (!row_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (lane == 0) bulk_wait_read1();
+          __syncwarp();
+          stage_store_b16(&tm.l, sStage + (2 + (n_out & 1)) * EPI_B16_BYTES, lane, v, n, row0);
+          ++n_out;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(acc2_empty_l);
+        bulk_wait_read0();  // the staging lives in the H buffers: every store has left smem before the next tile writes H
+      }
+      __syncwarp();
+      asm volatile("bar.sync 9, 256;" ::: "memory");  // ... for all eight epilogue warps
+    }
+    if (lane == 0) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while its peer can still signal its barriers or read its smem
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace mlp
+
+// JYUTVOICE_B200_MLP_PAIR=0: the single-CTA fused kernel instead of the CTA-pair one
+static inline bool mlp_pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_MLP_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // LNX [M_alloc, 256] bf16 (in: norm3(x); out: next norm1(x) when gamma != nullptr), X 16-bit stream in (fp16), `out`
 // = X (fp16, out_half = 1) or the bf16 copy for the next conv (out_half = 0).  W1 [1024, 256], W2 [256, 1024] bf16 K-major.
 static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const void* W1, const float* b1, const void* W2,
                                     const float* b2, const void* x_in, void* out, int out_half, const float* gamma,
                                     const float* beta, void* lnx_out, const int* frame_row, long M_alloc, int num_sms,
-                                    double algo_flops, cudaStream_t st) {
+                                    double algo_flops, int* sat_flag, cudaStream_t st) {
   static unsigned long long attr = 0;
-  if (first_use_on_device(attr))
+  if (first_use_on_device(attr)) {
     JV_CUDA(cudaFuncSetAttribute(mlp::mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+    JV_CUDA(cudaFuncSetAttribute(mlp::mlp_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::PAIR_SMEM_BYTES));
+  }
+  const bool pair = mlp_pair_mode() && num_sms % 2 == 0 && M_alloc / tc::BLOCK_M >= 2;
   JV_REQUIRE(mlp::SMEM_BYTES <= tc::SMEM_LIMIT, JV_ERR_STATE, "fused MLP: shared memory budget exceeded");
   mlp::Maps tm;
   tm.a = cache.get(lnx_in, 256, M_alloc, 256 * 2, 64, 128, 0);
-  tm.w1 = cache.get(W1, 256, 1024, 256 * 2, 64, 128, 0);
+  tm.w1 = cache.get(W1, 256, 1024, 256 * 2, 64, pair ? 64 : 128, 0);
   tm.w2 = cache.get(W2, 1024, 256, 1024 * 2, 64, 128, 0);
   tm.r = cache.get(x_in, 256, M_alloc, 256 * 2, 32, 32, 2);
   tm.o = cache.get(out, 256, M_alloc, 256 * 2, 32, 32, 2);
@@ -379,6 +739,7 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
   p.beta = beta;
   p.frame_row = frame_row;
   p.out_half = out_half;
+  p.sat_flag = sat_flag;
   ProfileState& ps = profile_state();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ps.on) {
@@ -388,7 +749,11 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(p.num_tiles < num_sms ? p.num_tiles : num_sms);
+  int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  if (pair) {
+    grid = 2 * std::min((p.num_tiles + 1) / 2, num_sms / 2);  // whole CTA pairs (the kernel carries __cluster_dims__(2,1,1))
+  }
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(mlp::THREADS);
   cfg.dynamicSmemBytes = mlp::SMEM_BYTES;
   cfg.stream = st;
@@ -397,7 +762,8 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
   lattr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = lattr;
   cfg.numAttrs = use_pdl() ? 1 : 0;
-  JV_CUDA(cudaLaunchKernelEx(&cfg, mlp::mlp_fused_kernel, tm, p));
+  if (pair) JV_CUDA(cudaLaunchKernelEx(&cfg, mlp::mlp_fused_pair_kernel, tm, p));
+  else JV_CUDA(cudaLaunchKernelEx(&cfg, mlp::mlp_fused_kernel, tm, p));
   JV_LAUNCHED();
   if (ps.on) {
     JV_CUDA(cudaEventRecord(e1, st));

@@ -19,7 +19,7 @@ import math
 
 import torch
 
-from ._tables import estimator_table, hift_table  # noqa: F401  (the single key/shape table)
+from ._tables import estimator_table, hift_table, text_encoder_table, duration_predictor_table  # noqa: F401  (the single key/shape tables)
 
 
 def _bias_shape(table, idx):
@@ -48,6 +48,8 @@ def _draw(table, seed, w_gain=math.sqrt(3.0), g_range=(0.8, 1.2), alpha_range=(0
             sd[key] = 1.0 + 0.1 * torch.randn(shape, generator=g)
         elif kind == "beta":
             sd[key] = 0.05 * torch.randn(shape, generator=g)
+        elif kind == "emb":
+            sd[key] = torch.randn(shape, generator=g) * shape[1] ** -0.5
         elif kind == "alpha":
             sd[key] = alpha_range[0] + (alpha_range[1] - alpha_range[0]) * torch.rand(shape, generator=g)
         elif kind == "wn_g":
@@ -116,6 +118,22 @@ def make_hift_state_dict(seed=4321, f0_bias=None):
     sd = _draw(hift_table(), seed, w_gain=1.0, g_range=(0.9, 1.1), alpha_range=(0.8, 1.2))
     if f0_bias is not None:
         sd["f0_predictor.classifier.bias"] = torch.full((1,), float(f0_bias))
+    return sd
+
+
+def make_text_encoder_state_dict(seed=2468, n_vocab=97, n_lang=4, n_tone=7):
+    """TextEncoder weights under the reference's keys (text_encoder.py:340-420).  The reference zero-initialises
+    prenet.proj (the prenet is the identity at construction); here it is drawn like every other conv so the branch counts."""
+    return _draw(text_encoder_table(n_vocab, n_lang, n_tone), seed, w_gain=1.0)
+
+
+def make_duration_predictor_state_dict(seed=1357):
+    """DurationPredictor weights (duration_predictor.py:26-46).  The output layer is drawn small around a bias of 0.35,
+    so exp(logw) lies in (1, 2) and every token lasts ceil(w) = 2 frames before `length_scale`: 50 tokens at
+    length_scale 3.0 give the ~300-frame utterances of BASELINE.json's configs deterministically."""
+    sd = _draw(duration_predictor_table(), seed, w_gain=1.0)
+    sd["proj.weight"] = sd["proj.weight"] * 0.15
+    sd["proj.bias"] = torch.full((1,), 0.35)
     return sd
 
 

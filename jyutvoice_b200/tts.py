@@ -2,11 +2,13 @@
 
   JyutVoiceTTS.synthesise  <- jyutvoice/models/jyutvoice_tts.py:108-253
 
-Same constructor arguments and the same returned dict.  The text encoder and the duration predictor are the
-caller's modules (the reference's own `TextEncoder` / `DurationPredictor`, built by its hyperpyyaml config):
-they run unchanged as PyTorch host code in front of the hot path.  The length
-regulation (integer indexing) uses the reference's torch ops one for one, so `mel_lengths` / `attn` are
-bit-exact; the CFM solve runs on the sm_100a library.  Supersets: any batch size (the reference raises for
+Same constructor arguments and the same returned dict.  `encoder` / `dp` are jyutvoice_b200.TextEncoder /
+DurationPredictor (text.py: the whole text front runs on the GPU, batched) or any modules with the reference's
+signatures (e.g. the reference's own classes: they then run as the caller's PyTorch code in front of the path).
+Length regulation: on CUDA the durations -> lengths -> alignment -> mu_y chain is three small kernels and a
+gather (text.length_regulate: no [B,T,Tx] x [B,Tx,80] matmul); on CPU tensors the reference's torch ops are
+kept one for one (host logic, used by the CPU tests).  Either way `mel_lengths` / `attn` are bit-exact.
+The CFM solve runs on the sm_100a library.  Supersets: any batch size (the reference raises for
 batch != 1: jyutvoice_tts.py:205-211) and `prompt_feat=None` / `prompt_h=None` defaults.
 """
 import datetime as dt
@@ -16,6 +18,7 @@ import torch.nn as nn
 from torch.nn import functional as F
 
 from .flow_matching import CausalConditionalCFM
+from . import text as _text
 
 
 def sequence_mask(length, max_length=None):
@@ -68,17 +71,23 @@ class JyutVoiceTTS(nn.Module):
         # :179-182
         x, mu_x, x_mask = self.encoder(x, x_lengths, lang, tone, word_pos, syllable_pos, spk_embed)
         logw = self.dp(x, x_mask, spk_embed)
-        # :184-187 (scale applied after the ceil; .long() truncates)
-        w = torch.exp(logw) * x_mask
-        w_ceil = torch.ceil(w) * length_scale
-        y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
-        y_max_length = y_lengths.max()
-        # :190-196
-        y_mask = sequence_mask(y_lengths, y_max_length).unsqueeze(1).to(x_mask.dtype)
-        attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
-        attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1)).unsqueeze(1)
-        # :199-203
-        mu_y = torch.matmul(attn.squeeze(1).transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)
+        if logw.device.type == "cuda":
+            # :184-203 as kernels: ceil / cumsum / lengths, then every mel frame gathers its token's 80-vector
+            mu_y, y_lengths, frame_token, _ = _text.length_regulate(logw, x_mask, mu_x, length_scale)
+            attn = _text.attn_from_frame_token(frame_token, x_mask.shape[-1], x_mask.dtype)
+            y_max_length = y_lengths.max()
+        else:
+            # :184-187 (scale applied after the ceil; .long() truncates)
+            w = torch.exp(logw) * x_mask
+            w_ceil = torch.ceil(w) * length_scale
+            y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+            y_max_length = y_lengths.max()
+            # :190-196
+            y_mask = sequence_mask(y_lengths, y_max_length).unsqueeze(1).to(x_mask.dtype)
+            attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
+            attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1)).unsqueeze(1)
+            # :199-203
+            mu_y = torch.matmul(attn.squeeze(1).transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)
         encoder_outputs = mu_y[:, :, :y_max_length]
         B = mu_y.shape[0]
         lens = [int(v) for v in y_lengths.cpu()]

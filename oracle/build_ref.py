@@ -2,7 +2,7 @@
 
 TEST / BASELINE INFRASTRUCTURE.  The reference is pure Python, so "building" it means compiling the modules the path
 imports (found by importing the path once through oracle/ref_shims.py and listing what was loaded from the reference
-tree) to sourceless `.pyc` files.  Only compiled outputs are written, only into oracle/_ref/ (git-ignored, shipped to
+tree) to sourceless bytecode files (`*.refbin`, CPython .pyc format).  Only compiled outputs are written, only into oracle/_ref/ (git-ignored, shipped to
 the GPU box by gpurun like our own .so): no reference source enters the repository.  `bench.py --impl reference` and
 bench.py's cpu_baseline leg import it there (kind "reference"); without it they fall back to the oracle port.
 
@@ -36,7 +36,9 @@ def build(verbose=False):
         shutil.rmtree(OUT)
     for f in sorted(files):
         rel = os.path.relpath(f, SRC_ROOT)
-        dst = os.path.join(OUT, rel + "c")  # sourceless layout: module.pyc next to where module.py would be
+        # compiled module next to where module.py would be; the suffix is not ".pyc" because snapshot tools (gpurun's
+        # among them) drop *.pyc files: oracle/ref_shims.py installs a finder that loads ".refbin" bytecode
+        dst = os.path.join(OUT, rel[:-3] + ".refbin")
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(f, cfile=dst, dfile=rel, doraise=True)
         if verbose:

@@ -60,18 +60,21 @@ def synth_inputs(seed, Tx):
 
 
 def synth_golden():
-    """Runs the reference's real TextEncoder + DurationPredictor + synthesise.  The encoder / dp outputs are stored so
-    the GPU test can stand in for those two (out-of-scope, host-side) modules without their 25 M weights."""
+    """Runs the reference's real TextEncoder + DurationPredictor + synthesise with the synthetic weights of
+    jyutvoice_b200/synthetic.py.  The encoder / dp outputs are stored too: they pin oracle/text_encoder.py and the GPU
+    text front, and let the CPU tests replay them."""
     import types
     ref_shims.install()
     from jyutvoice.models.jyutvoice_tts import JyutVoiceTTS
     from jyutvoice.models.text_encoder import TextEncoder
     from jyutvoice.models.duration_predictor import DurationPredictor
-    torch.manual_seed(1234)
     enc_params = types.SimpleNamespace(n_feats=80, n_channels=192, filter_channels=768, filter_channels_dp=256, n_heads=2,
                                        n_layers=6, kernel_size=3, p_dropout=0.1, gin_channels=192, prenet=True)
     encoder = TextEncoder(encoder_type="RoPE Encoder", encoder_params=enc_params, n_vocab=97, n_lang=4, n_tone=7)
     dp = DurationPredictor(in_channels=576, filter_channels=256, kernel_size=3, p_dropout=0.1, gin_channels=192)
+    # deterministic synthetic weights under the reference's keys (strict load = the key tables are the reference's)
+    encoder.load_state_dict(weights.make_text_encoder_state_dict(), strict=True)
+    dp.load_state_dict(weights.make_duration_predictor_state_dict(), strict=True)
     cfm = ref_shims.build_reference_cfm()
     cfm.load_state_dict(weights.make_estimator_state_dict(), strict=True)
     tts = JyutVoiceTTS(encoder=encoder, decoder=cfm, dp=dp, output_size=80, spk_embed_dim=192)

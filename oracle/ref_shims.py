@@ -101,6 +101,29 @@ def _mod(name, **attrs):
 _installed = False
 
 
+class _BuiltRefFinder:
+    """Imports `jyutvoice.*` from the byte-compiled tree oracle/build_ref.py wrote (<root>/jyutvoice/.../module.refbin,
+    CPython .pyc format under another suffix)."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if fullname != "jyutvoice" and not fullname.startswith("jyutvoice."):
+            return None
+        rel = os.path.join(self.root, *fullname.split("."))
+        if os.path.isfile(os.path.join(rel, "__init__.refbin")):
+            f = os.path.join(rel, "__init__.refbin")
+            loader = importlib.machinery.SourcelessFileLoader(fullname, f)
+            return importlib.util.spec_from_file_location(fullname, f, loader=loader, submodule_search_locations=[rel])
+        if os.path.isfile(rel + ".refbin"):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, rel + ".refbin")
+            return importlib.util.spec_from_file_location(fullname, rel + ".refbin", loader=loader)
+        return None
+
+
 def install():
     """Register stand-in modules so that `import jyutvoice.flow...` works from REF_ROOT."""
     global _installed
@@ -108,7 +131,9 @@ def install():
         return
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REF_ROOT}")
-    if REF_ROOT not in sys.path:
+    if os.path.isfile(os.path.join(REF_ROOT, "jyutvoice", "__init__.refbin")):
+        sys.meta_path.insert(0, _BuiltRefFinder(REF_ROOT))  # the byte-compiled copy (oracle/_ref)
+    elif REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
 
     # jyutvoice.utils: skip its __init__ (pulls hydra/lightning/...): bare package object.

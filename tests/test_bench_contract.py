@@ -27,7 +27,7 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["metric"] == "audio_seconds_per_second" and d["unit"] == "audio-s/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["gpu_launches"] == 0
     assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"]
-    built = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "jyutvoice")) or os.path.isdir("/root/reference/jyutvoice")
+    built = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "jyutvoice", "__init__.refbin")) or os.path.isdir("/root/reference/jyutvoice")
     assert d["cpu_baseline"]["kind"] == ("reference" if built else "port")  # the reference's own modules when oracle/_ref exists
     assert d["config"]["precision"] == "fp32" and d["dtype"] == "f32" and d["p50_ms"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -140,3 +140,23 @@ def test_lengths_golden():
         attn_mask = x_mask[:, 0, :, None] * y_mask[:, 0, None, :]
         path = ol.generate_path(w_ceil[:, 0], attn_mask)
         assert np.array_equal(path[:, None], g[f"c{ci}_attn"])
+
+
+@pytest.mark.parametrize("name", ["synth_c1", "synth_prompt"])
+def test_text_front_golden(name):
+    """oracle/text_encoder.py against the reference's real TextEncoder / DurationPredictor outputs (synthetic weights)."""
+    from oracle import text_encoder as ot
+    from oracle.make_golden import synth_inputs
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    inp = synth_inputs(int(g["seed"]), int(g["Tx"]))
+    esd, dsd = weights.make_text_encoder_state_dict(), weights.make_duration_predictor_state_dict()
+    with torch.no_grad():
+        x, mu, mask = ot.text_encoder_forward(esd, *inp)
+        logw = ot.duration_predictor_forward(dsd, x, mask, inp[-1])
+        mu_y, y_len, attn = ot.regulate(logw, mask, mu, float(g["length_scale"]))
+    assert (x - torch.from_numpy(g["enc_x"])).abs().max().item() <= 1e-5
+    assert (mu - torch.from_numpy(g["enc_mu"])).abs().max().item() <= 1e-5
+    assert (logw - torch.from_numpy(g["logw"])).abs().max().item() <= 1e-5
+    assert np.array_equal(y_len.numpy(), g["mel_lengths"])
+    assert np.array_equal(attn.numpy().astype(np.uint8), g["attn"])
+    assert (mu_y - torch.from_numpy(g["encoder_outputs"])).abs().max().item() <= 1e-5
