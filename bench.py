@@ -1,11 +1,12 @@
 #!/usr/bin/env python
-"""Headline benchmark: audio-seconds generated per second (1/RTF) of the CFM (10 NFE, CFG) + HiFT hot
-path on synthetic utterances of BASELINE.json's throughput config (batch 64 per GPU, ~6 s each, bf16).
+"""Headline benchmark: audio-seconds generated per second (1/RTF) of `JyutVoiceTTS.synthesise` (text encoder,
+duration predictor, length regulator, CFM with 10 NFE and CFG) + `HiFTGenerator.inference` on synthetic token
+sequences of BASELINE.json's throughput config (batch 64 per GPU, ~50 tokens = ~6 s each, bf16).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (torchrun for N > 1)
   python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the reference's own modules (oracle/_ref) on host cores
 
-One "step" = one pass of the hot path over one batch: CausalConditionalCFM.forward -> HiFTGenerator.inference.
+One "step" = one pass of the hot path over one batch: JyutVoiceTTS.synthesise -> HiFTGenerator.inference.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -63,6 +64,26 @@ def make_workload(batch, frames, seed):
     return lens, Tmax, mu, spks
 
 
+LENGTH_SCALE = 3.0  # ~50 tokens at length_scale 3.0 => ~6 s
+
+
+def make_token_workload(batch, tokens, seed):
+    """Synthetic token sequences of BASELINE.json's shape: Tx in U{0.9 n .. 1.1 n} tokens per utterance,
+    ids / language / tone / word and syllable position streams and a 192-d speaker embedding drawn per utterance.
+    With the synthetic duration predictor every token lasts 2 frames, x length_scale 3.0: 50 tokens -> 300 mel frames."""
+    g = torch.Generator().manual_seed(seed)
+    lo, hi = int(tokens * 0.9), int(tokens * 1.1)
+    x_lens = torch.randint(lo, hi + 1, (batch,), generator=g)
+    Tx = hi
+    ri = lambda a, b: torch.randint(a, b, (batch, Tx), generator=g)
+    x, lang, tone, wp, sp = ri(1, 97), ri(0, 4), ri(0, 7), ri(0, 4), ri(0, 4)
+    spk = torch.randn(batch, 192, generator=g)
+    keep = torch.arange(Tx)[None, :] < x_lens[:, None]
+    for t in (x, lang, tone, wp, sp):
+        t.mul_(keep)
+    return {"x": x, "x_lengths": x_lens, "lang": lang, "tone": tone, "word_pos": wp, "syllable_pos": sp, "spk_embed": spk}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (NVML)."""
 
@@ -114,69 +135,87 @@ class ClockSampler(threading.Thread):
 
 
 class CpuArm:
-    """The reference's CPU implementation of the path, batch-1 loop (its only mode), fp32, torch CPU threads.
+    """The reference's CPU implementation of the path, batch-1 loop (its only mode), fp32, torch CPU threads: one utterance
+    = JyutVoiceTTS.synthesise (text encoder, duration predictor, length regulation, CFM) + HiFTGenerator.inference.
     kind "reference": the reference's own modules imported from oracle/_ref (byte-compiled from /root/reference by
     oracle/build_ref.py; the source tree itself when it is present) through oracle/ref_shims.py.
-    kind "port": the oracle restatement (oracle/estimator.py, oracle/hift.py), used only when oracle/_ref is absent."""
+    kind "port": the oracle restatement (oracle/text_encoder.py, estimator.py, hift.py), used only when oracle/_ref is absent."""
 
-    def __init__(self, est_sd, hift_sd):
+    def __init__(self, sds):
         from jyutvoice_b200 import synthetic
         self.kind = "port"
-        self.est_sd, self.hift_sd = est_sd, hift_sd
+        self.sds = sds
         self.nb = synthetic.noise_bank()
         try:
             from oracle import ref_shims
             if ref_shims.reference_available():
-                self.cfm = ref_shims.build_reference_cfm()
-                self.cfm.load_state_dict(est_sd, strict=True)
+                cfm = ref_shims.build_reference_cfm()
+                cfm.load_state_dict(sds["est"], strict=True)
+                self.tts = ref_shims.build_reference_tts(cfm)
+                self.tts.encoder.load_state_dict(sds["enc"], strict=True)
+                self.tts.dp.load_state_dict(sds["dp"], strict=True)
+                self.tts.spk_embed_affine_layer.load_state_dict(sds["aff"])
                 self.hift = ref_shims.build_reference_hift()
-                self.hift.load_state_dict(hift_sd, strict=True)
+                self.hift.load_state_dict(sds["hift"], strict=True)
                 self.kind = "reference"
         except Exception as e:  # fall back to the port, and say why
             print(f"bench.py: reference arm falls back to the oracle port ({type(e).__name__}: {e})", file=sys.stderr)
             self.kind = "port"
 
-    def one_utterance(self, frames, nfe, seed):
-        """CFM solve + HiFT inference of one synthetic utterance; returns its audio seconds."""
-        g = torch.Generator().manual_seed(seed)
-        mu = torch.randn(1, 80, frames, generator=g)
-        spks = torch.randn(1, 80, generator=g)
+    def one_utterance(self, tokens, nfe, seed):
+        """synthesise + HiFT inference of one synthetic utterance; returns its audio seconds."""
+        w = make_token_workload(1, tokens, seed)
+        Tx = int(w["x_lengths"][0])
+        inp = [w[k][:, :Tx] for k in ("x",)] + [w["x_lengths"]] + [w[k][:, :Tx] for k in ("lang", "tone", "word_pos", "syllable_pos")] + [w["spk_embed"]]
         if self.kind == "reference":
             with torch.inference_mode():
-                mel, _ = self.cfm(mu, torch.ones(1, 1, frames), nfe, 1.0, spks, torch.zeros(1, 80, frames))
-                self.hift.inference(speech_feat=mel)
+                out = self.tts.synthesise(*inp, prompt_feat=None, prompt_h=None, n_timesteps=nfe, temperature=1.0, length_scale=LENGTH_SCALE)
+                self.hift.inference(speech_feat=out["decoder_outputs"])
+            frames = int(out["mel_lengths"][0])
         else:
-            from oracle import estimator as oe, hift as oh
+            from oracle import estimator as oe, hift as oh, text_encoder as ot
+            import torch.nn.functional as F
             with torch.no_grad():
-                mel = oe.cfm_forward(self.est_sd, self.nb, mu, torch.ones(1, 1, frames), nfe, 1.0, spks, torch.zeros(1, 80, frames))
-                oh.inference(self.hift_sd, mel, oh.draw_source_rng(1, 480 * frames, g))
+                hx, mu_x, mask = ot.text_encoder_forward(self.sds["enc"], *inp)
+                logw = ot.duration_predictor_forward(self.sds["dp"], hx, mask, inp[-1])
+                mu_y, y_len, _ = ot.regulate(logw, mask, mu_x, LENGTH_SCALE)
+                frames = int(y_len[0])
+                c = F.linear(F.normalize(inp[-1], dim=1), self.sds["aff"]["weight"], self.sds["aff"]["bias"])
+                mel = oe.cfm_forward(self.sds["est"], self.nb, mu_y, torch.ones(1, 1, frames), nfe, 1.0, c, torch.zeros(1, 80, frames))
+                oh.inference(self.sds["hift"], mel, oh.draw_source_rng(1, 480 * frames, torch.Generator().manual_seed(seed)))
         return frames / FRAMES_PER_SEC
 
-    def describe(self, n_utts, frames, nfe, cores):
+    def describe(self, n_utts, tokens, nfe, cores):
         what = "the reference's own modules (oracle/_ref)" if self.kind == "reference" else "oracle port"
-        return (f"{n_utts} utterance(s) of {frames} frames, {what}, batch-1 loop (the reference's only mode), fp32, "
-                f"{nfe} NFE + HiFT, torch CPU with {cores} threads")
+        return (f"{n_utts} utterance(s) of ~{tokens} tokens (~{6 * tokens} frames), {what}, batch-1 loop (the reference's only mode), "
+                f"fp32, synthesise ({nfe} NFE) + HiFT, torch CPU with {cores} threads")
+
+
+def all_state_dicts():
+    from jyutvoice_b200 import synthetic
+    return {"est": synthetic.make_estimator_state_dict(), "hift": synthetic.make_hift_state_dict(),
+            "enc": synthetic.make_text_encoder_state_dict(), "dp": synthetic.make_duration_predictor_state_dict(),
+            "aff": synthetic.make_spk_affine_state_dict()}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from jyutvoice_b200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    arm = CpuArm(synthetic.make_estimator_state_dict(), synthetic.make_hift_state_dict())
+    arm = CpuArm(all_state_dicts())
     for w in range(args.warmup):
-        arm.one_utterance(min(args.frames, 100), args.nfe, w)
+        arm.one_utterance(min(args.tokens, 16), args.nfe, w)
     times = []
     audio = 0.0
     for k in range(args.steps):
         t0 = time.perf_counter()
-        audio += arm.one_utterance(args.frames, args.nfe, 100 + k)
+        audio += arm.one_utterance(args.tokens, args.nfe, 100 + k)
         times.append(time.perf_counter() - t0)
     dt = sum(times)
     value = audio / dt
-    sample = arm.describe(args.steps, args.frames, args.nfe, cores)
+    sample = arm.describe(args.steps, args.tokens, args.nfe, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(1, args.steps), "p50_ms": sorted(times)[len(times) // 2] * 1e3,
@@ -190,26 +229,23 @@ def run_reference(args):
 
 
 def workload_config(args, precision=None):
-    return {"workload": f"BASELINE configs[4] per-GPU slice: batch {args.batch} utterances x ~{args.frames / FRAMES_PER_SEC:.0f} s "
-                        f"({int(args.frames * 0.9)}..{int(args.frames * 1.1)} mel frames), n_timesteps={args.nfe}, CFG 0.7, "
-                        f"CFM solve + HiFT vocoder",
-            "batch_per_gpu": args.batch, "frames": args.frames, "n_timesteps": args.nfe, "precision": precision or args.precision,
+    return {"workload": f"BASELINE configs[4] per-GPU slice: batch {args.batch} synthetic token sequences of {int(args.tokens * 0.9)}.."
+                        f"{int(args.tokens * 1.1)} tokens (length_scale {LENGTH_SCALE}: {6 * int(args.tokens * 0.9)}..{6 * int(args.tokens * 1.1)} mel "
+                        f"frames, ~{6 * args.tokens / FRAMES_PER_SEC:.0f} s), n_timesteps={args.nfe}, CFG 0.7, JyutVoiceTTS.synthesise "
+                        f"(text encoder, duration predictor, length regulator, CFM) + HiFT vocoder",
+            "batch_per_gpu": args.batch, "tokens": args.tokens, "frames": 6 * args.tokens, "n_timesteps": args.nfe,
+            "precision": precision or args.precision,
             "l2": "no explicit flush: per-step working set (185 MB bf16 weights + >1 GB activations) exceeds the 126 MB L2",
-            "weights": "random-init (jyutvoice_b200.synthetic, PyTorch-default statistics)"}
+            "weights": "random-init (jyutvoice_b200.synthetic, PyTorch-default statistics; the duration predictor's output layer "
+                       "is centred so that every token lasts 2 frames before length_scale)"}
 
 
-def global_workload(world, batch, frames):
+def global_workload(world, batch, tokens):
     """BASELINE config 5: a fixed set of 512 synthetic utterances, 64 per GPU.  Slice r of the set is
-    make_workload(batch, frames, 1000 + r); a run on `world` GPUs takes the first `world` slices and shards them with
-    sharding.shard_utterances (at world = 1 that is exactly slice 0 in its own order)."""
-    lens, mus, spk = [], [], []
-    Tmax = int(frames * 1.1)
-    for r in range(world):
-        l, _, mu, sp = make_workload(batch, frames, 1000 + r)
-        lens += l
-        mus.append(mu)
-        spk.append(sp)
-    return lens, Tmax, torch.cat(mus), torch.cat(spk)
+    make_token_workload(batch, tokens, 1000 + r); a run on `world` GPUs takes the first `world` slices and shards them with
+    sharding.shard_utterances (at world = 1 that is exactly slice 0 in its own order).  Mel lengths are 6 frames per token."""
+    parts = [make_token_workload(batch, tokens, 1000 + r) for r in range(world)]
+    return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
 
 
 def p50(xs):
@@ -217,27 +253,41 @@ def p50(xs):
     return s[len(s) // 2]
 
 
-def small_latency(precision, est_sd, hift_sd, dev, frames=99, nfe=10, reps=7):
-    """BASELINE config 1 (one ~2 s utterance, batch 1, 10 NFE): p50 wall latency of CFM + HiFT through the Python API,
-    host tensors in, waveform back on the host."""
-    from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, HiFTGenerator
+def build_tts(precision, sds, dev):
+    from jyutvoice_b200 import (CausalConditionalCFM, CausalConditionalDecoder, DurationPredictor, HiFTGenerator, JyutVoiceTTS,
+                                TextEncoder)
+    params = dict(n_feats=80, n_channels=192, filter_channels=768, filter_channels_dp=256, n_heads=2, n_layers=6, kernel_size=3,
+                  p_dropout=0.1, gin_channels=192, prenet=True)
+    enc = TextEncoder("RoPE Encoder", params, n_vocab=97, n_lang=4, n_tone=7)
+    enc.load_state_dict(sds["enc"], strict=True)
+    dp = DurationPredictor(in_channels=576, filter_channels=256, kernel_size=3, p_dropout=0.1, gin_channels=192)
+    dp.load_state_dict(sds["dp"], strict=True)
     cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision=precision))
-    cfm.load_state_dict(est_sd, strict=True)
-    cfm = cfm.to(dev)
+    cfm.load_state_dict(sds["est"], strict=True)
+    tts = JyutVoiceTTS(encoder=enc, decoder=cfm, dp=dp)
+    tts.spk_embed_affine_layer.load_state_dict(sds["aff"])
     hift = HiFTGenerator(precision=precision)
-    hift.load_state_dict(hift_sd, strict=True)
-    hift = hift.to(dev)
-    g = torch.Generator().manual_seed(0)
-    mu = torch.randn(1, 80, frames, generator=g).pin_memory()
-    spks = torch.randn(1, 80, generator=g).pin_memory()
-    out = torch.empty((1, 480 * frames)).pin_memory()
+    hift.load_state_dict(sds["hift"], strict=True)
+    return tts.to(dev), hift.to(dev)
+
+
+TOKEN_KEYS = ("x", "x_lengths", "lang", "tone", "word_pos", "syllable_pos", "spk_embed")
+
+
+def small_latency(precision, sds, dev, tokens=16, nfe=10, reps=7):
+    """BASELINE config 1 (one ~2 s utterance, batch 1, 10 NFE): p50 wall latency of synthesise + HiFT through the Python API,
+    host tensors in, waveform back on the host.  16 tokens x 6 frames = 96 frames."""
+    tts, hift = build_tts(precision, sds, dev)
+    w = make_token_workload(1, tokens, 0)
+    pin = {k: v.pin_memory() for k, v in w.items()}
     ts = []
     for i in range(reps + 2):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        mel, _ = cfm(mu.to(dev, non_blocking=True), None, nfe, 1.0, spks.to(dev, non_blocking=True), None, lengths=[frames])
-        wav, _ = hift.inference(mel, lengths=[frames])
-        out.copy_(wav, non_blocking=True)
+        d = [pin[k].to(dev, non_blocking=True) for k in TOKEN_KEYS]
+        out = tts.synthesise(*d, n_timesteps=nfe, length_scale=LENGTH_SCALE)
+        wav, _ = hift.inference(out["decoder_outputs"], lengths=[int(v) for v in out["mel_lengths"].cpu()])
+        wav.cpu()
         torch.cuda.synchronize()
         if i >= 2:
             ts.append((time.perf_counter() - t0) * 1e3)
@@ -246,7 +296,7 @@ def small_latency(precision, est_sd, hift_sd, dev, frames=99, nfe=10, reps=7):
 
 def run_ours(args):
     import torch.distributed as dist
-    from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, HiFTGenerator, synthetic, sharding, _lib
+    from jyutvoice_b200 import sharding, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -259,34 +309,31 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    est_sd = synthetic.make_estimator_state_dict()
-    hift_sd = synthetic.make_hift_state_dict()
-    cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision=args.precision))
-    cfm.load_state_dict(est_sd, strict=True)
-    cfm = cfm.to(dev)
-    hift = HiFTGenerator(precision=args.precision)
-    hift.load_state_dict(hift_sd, strict=True)
-    hift = hift.to(dev)
+    sds = all_state_dicts()
+    tts, hift = build_tts(args.precision, sds, dev)
 
     # the sweep's utterance set, sharded across the ranks (weak scaling: 64 utterances per GPU)
-    all_lens, Tmax, all_mu, all_spks = global_workload(world, args.batch, args.frames)
-    total = len(all_lens)
-    plan = sharding.shard_utterances(all_lens, world)
+    allw = global_workload(world, args.batch, args.tokens)
+    all_frames = [6 * int(v) for v in allw["x_lengths"]]  # 2 frames per token x length_scale 3.0 (synthetic duration predictor)
+    total = len(all_frames)
+    plan = sharding.shard_utterances(all_frames, world)
     mine = plan[rank]
-    lens = [all_lens[i] for i in mine]
-    audio_s = sum(lens) / FRAMES_PER_SEC
-    mu_pin, spks_pin = all_mu[mine].contiguous().pin_memory(), all_spks[mine].contiguous().pin_memory()
-    del all_mu, all_spks
-    mu_d, spks_d = mu_pin.to(dev), spks_pin.to(dev)
+    pin = {k: allw[k][mine].contiguous().pin_memory() for k in TOKEN_KEYS}
+    del allw
+    res = {k: v.to(dev) for k, v in pin.items()}
     n_mine = len(mine)
+    Tmax = 6 * int(args.tokens * 1.1)
     wav_pin = torch.empty((n_mine, 480 * Tmax), dtype=torch.float32).pin_memory()
-    wav_lens = torch.tensor([480 * l for l in lens], dtype=torch.int64, device=dev)
+    state = {}
 
-    def step(mu, spks):
-        mel, _ = cfm(mu, None, args.nfe, 1.0, spks, None, lengths=lens)
-        wav, _ = hift.inference(mel, lengths=lens)
+    def step(d):
+        out = tts.synthesise(*[d[k] for k in TOKEN_KEYS], n_timesteps=args.nfe, temperature=1.0, length_scale=LENGTH_SCALE)
+        lens = [int(v) for v in out["mel_lengths"].cpu()]  # (synthesise has already read them once: the length regulator's host read)
+        wav, _ = hift.inference(out["decoder_outputs"], lengths=lens)
         if world > 1:  # the only collective of the path: every rank ends up with all waveforms, in the set's order
-            sharding.gather_waveforms(wav, wav_lens, mine, total, 480 * Tmax)
+            wl = torch.tensor([480 * l for l in lens], dtype=torch.int64, device=dev)
+            sharding.gather_waveforms(wav, wl, mine, total, 480 * Tmax)
+        state["lens"] = lens
         return wav
 
     def barrier():
@@ -295,8 +342,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step(mu_d, spks_d)
+        step(res)
     barrier()
+    lens = state["lens"]
+    assert lens == [all_frames[i] for i in mine], "synthetic duration predictor: every token should last 6 frames"
+    audio_s = sum(lens) / FRAMES_PER_SEC
 
     # ---- timed region 1: device-resident inputs (value); one event per step boundary gives the per-step p50
     sampler = ClockSampler(local)
@@ -306,7 +356,7 @@ def run_ours(args):
     barrier()
     evs[0].record()
     for k in range(args.steps):
-        step(mu_d, spks_d)
+        step(res)
         evs[k + 1].record()
     barrier()
     ms = evs[0].elapsed_time(evs[-1])
@@ -319,16 +369,16 @@ def run_ours(args):
     t_all = time.perf_counter()
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        mu = mu_pin.to(dev, non_blocking=True)
-        spks = spks_pin.to(dev, non_blocking=True)
-        wav = step(mu, spks)
-        wav_pin.copy_(wav, non_blocking=True)
+        d = {k: pin[k].to(dev, non_blocking=True) for k in TOKEN_KEYS}
+        wav = step(d)
+        wav_pin[:, : wav.shape[1]].copy_(wav, non_blocking=True)
         torch.cuda.synchronize()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     barrier()
     ms_e2e = (time.perf_counter() - t_all) * 1e3
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    wav_cols = 480 * max(lens)
 
     # ---- roofline of the dominant kernel: events around every tcgen05 GEMM launch, same steps
     kms, kfl, kn = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
@@ -336,13 +386,13 @@ def run_ours(args):
     if args.precision == "bf16":
         _lib.check(L.jv_profile_begin())
         for _ in range(max(1, min(args.steps, 2))):
-            step(mu_d, spks_d)
+            step(res)
         _lib.check(L.jv_profile_end(ctypes.byref(kms), ctypes.byref(kfl), ctypes.byref(kn)))
         peaks = load_peaks()
         achieved = kfl.value / (kms.value * 1e-3) / 1e12 if kms.value > 0 else 0.0
         nprof = max(1, min(args.steps, 2))
         traffic, traffic_src = load_traffic()
-        roof = {"bound": "tensor", "kernel": "gemm_taps_tc_kernel (tcgen05 bf16, all conv / linear contractions)",
+        roof = {"bound": "tensor", "kernel": "gemm_taps_tc_kernel + mlp_fused_pair_kernel (tcgen05 bf16: all conv / linear contractions)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
                 "traffic_source": traffic_src, "peak_source": peaks["src"] + " sustained bf16",
@@ -372,8 +422,8 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "p50_ms": p50(step_ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mu_pin.numel() * 4 + spks_pin.numel() * 4,
-                    "d2h_bytes_per_step": wav_pin.numel() * 4, "ms_per_step": ms_e2e / args.steps, "p50_ms": p50(e2e_ms)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pin.values()),
+                    "d2h_bytes_per_step": n_mine * wav_cols * 4 + n_mine * 8, "ms_per_step": ms_e2e / args.steps, "p50_ms": p50(e2e_ms)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "audio_seconds_per_step": audio_total,
@@ -386,43 +436,37 @@ def run_ours(args):
         if world == 1 and not args.no_extra:
             # (rank 0, single-GPU runs only: the multi-GPU launches stay short)
             extra = {}
-            del cfm, hift
+            del tts, hift
             torch.cuda.empty_cache()
-            extra["config1_latency_p50_ms"] = {"workload": "BASELINE configs[0]: one utterance of 99 frames (~2 s), batch 1, 10 NFE, "
-                                                           "CFM + HiFT, host in / host out",
-                                               "bf16": small_latency("bf16", est_sd, hift_sd, dev),
-                                               "fp32": small_latency("fp32", est_sd, hift_sd, dev)}
+            extra["config1_latency_p50_ms"] = {"workload": "BASELINE configs[0]: one utterance of 16 tokens = 96 frames (~2 s), batch 1, "
+                                                           "10 NFE, synthesise + HiFT, host in / host out",
+                                               "bf16": small_latency("bf16", sds, dev), "fp32": small_latency("fp32", sds, dev)}
             if args.precision == "bf16":  # the <= 1e-3 / >= 60 dB mode on the headline workload: one timed step
-                cfm32 = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision="fp32"))
-                cfm32.load_state_dict(est_sd, strict=True)
-                cfm32 = cfm32.to(dev)
-                hift32 = HiFTGenerator(precision="fp32")
-                hift32.load_state_dict(hift_sd, strict=True)
-                hift32 = hift32.to(dev)
+                tts32, hift32 = build_tts("fp32", sds, dev)
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 for i in range(2):
                     if i == 1:
                         f0.record()
-                    mel, _ = cfm32(mu_d, None, args.nfe, 1.0, spks_d, None, lengths=lens)
-                    hift32.inference(mel, lengths=lens)
+                    out = tts32.synthesise(*[res[k] for k in TOKEN_KEYS], n_timesteps=args.nfe, length_scale=LENGTH_SCALE)
+                    hift32.inference(out["decoder_outputs"], lengths=lens)
                 f1.record()
                 torch.cuda.synchronize()
                 ms32 = f0.elapsed_time(f1)
                 extra["fp32_mode"] = {"value": audio_s / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32, "steps": 1,
                                       "note": "same workload, precision fp32 (the mel <= 1e-3 / wav >= 60 dB mode)"}
-                del cfm32, hift32
+                del tts32, hift32
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            arm = CpuArm(est_sd, hift_sd)
-            arm.one_utterance(100, args.nfe, 0)  # warm-up
+            arm = CpuArm(sds)
+            arm.one_utterance(16, args.nfe, 0)  # warm-up
             t0 = time.perf_counter()
             n_utts = 2
-            audio = sum(arm.one_utterance(args.frames, args.nfe, 10 + i) for i in range(n_utts))
+            audio = sum(arm.one_utterance(args.tokens, args.nfe, 10 + i) for i in range(n_utts))
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": audio / dt, "unit": UNIT, "cores": cores, "kind": arm.kind,
-                                    "sample": arm.describe(n_utts, args.frames, args.nfe, cores)}
+                                    "sample": arm.describe(n_utts, args.tokens, args.nfe, cores)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -436,7 +480,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--tokens", type=int, default=50, help="mean tokens per utterance (6 mel frames each: 50 -> ~300 frames, ~6 s)")
     ap.add_argument("--nfe", type=int, default=10)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

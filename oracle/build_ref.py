@@ -27,6 +27,7 @@ def build(verbose=False):
     ref_shims.REF_ROOT = SRC_ROOT
     ref_shims.build_reference_cfm()
     ref_shims.build_reference_hift()
+    ref_shims.build_reference_tts()  # text encoder, duration predictor, JyutVoiceTTS.synthesise
     files = set()
     for name, mod in list(sys.modules.items()):
         f = getattr(mod, "__file__", None)

@@ -204,3 +204,19 @@ def build_reference_hift():
                          source_resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
                          lrelu_slope=0.1, audio_limit=0.99, f0_predictor=f0)
     return hift.eval()
+
+
+def build_reference_tts(cfm=None):
+    """Reference JyutVoiceTTS (jyutvoice/models/jyutvoice_tts.py) with its own TextEncoder / DurationPredictor and the
+    configs/base.yaml encoder_params; random init (load the synthetic state dicts on top)."""
+    install()
+    from jyutvoice.models.jyutvoice_tts import JyutVoiceTTS
+    from jyutvoice.models.text_encoder import TextEncoder
+    from jyutvoice.models.duration_predictor import DurationPredictor
+    enc_params = types.SimpleNamespace(n_feats=80, n_channels=192, filter_channels=768, filter_channels_dp=256, n_heads=2,
+                                       n_layers=6, kernel_size=3, p_dropout=0.1, gin_channels=192, prenet=True)
+    encoder = TextEncoder(encoder_type="RoPE Encoder", encoder_params=enc_params, n_vocab=97, n_lang=4, n_tone=7)
+    dp = DurationPredictor(in_channels=576, filter_channels=256, kernel_size=3, p_dropout=0.1, gin_channels=192)
+    tts = JyutVoiceTTS(encoder=encoder, decoder=cfm if cfm is not None else build_reference_cfm(), dp=dp, output_size=80,
+                       spk_embed_dim=192)
+    return tts.eval()

@@ -14,7 +14,7 @@ REQUIRED = {"impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_
 def run(extra_env=None):
     env = dict(os.environ, **(extra_env or {}))
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--frames", "20", "--nfe", "1"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+                          "--tokens", "4", "--nfe", "1"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     return [l for l in out.stdout.splitlines() if l.strip()]
 
