@@ -203,6 +203,8 @@ struct GemmDesc {
   int tap_shift[MAX_TAPS];
   int K_tap;           // K per tap (same for all taps)
   const void* W;       // [N, n_taps*K_tap] K-major, activation type
+  const float* W_hi;   // fp32 engines only: W split for 3xTF32 (W_hi = W with the low 13 mantissa bits cleared, W_lo = W - W_hi);
+  const float* W_lo;   //   null -> the FFMA engine runs the contraction
   int M, N;
   // epilogue, in this order (every step optional):
   //   v = acc + bias[n]

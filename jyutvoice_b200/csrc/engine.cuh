@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tf32.cuh"
 #include "kernels.cuh"
 
 namespace jv {
@@ -40,11 +41,19 @@ struct Engine {
     JV_LAUNCHED();
   }
 
-  // FFMA path: GEMM with the element-wise part of the epilogue, LayerNorms as separate row kernels.
+  // One contraction with the element-wise part of the epilogue on an fp32-accurate engine: 3xTF32 on the tensor cores
+  // (gemm_tf32.cuh) when the operands are fp32 and the shape fits, else the FFMA kernel.
+  template <typename TA>
+  void gemm_plain(const GemmDesc& g, cudaStream_t st) {
+    if (sizeof(TA) == 4 && use_tf32() && gemm_tf32_supported(g)) launch_gemm_tf32(g, tmaps, num_sms, st);
+    else launch_gemm_simt<TA>(g, st);
+  }
+
+  // fp32 path: GEMM with the element-wise part of the epilogue, LayerNorms as separate row kernels.
   template <typename TA>
   void gemm_lowered(const GemmDesc& g, cudaStream_t st) {
     if (!g.ln1_gamma && !g.ln2_gamma) {
-      launch_gemm_simt<TA>(g, st);
+      gemm_plain<TA>(g, st);
       return;
     }
     JV_REQUIRE(g.N == 256 && g.o_stride == 1 && g.o_off == 0, JV_ERR_INVALID, "LayerNorm epilogue needs N == 256, dense rows");
@@ -54,7 +63,7 @@ struct Engine {
       a.ln1_gamma = a.ln1_beta = a.ln2_gamma = a.ln2_beta = nullptr;
       a.act = ACT_NONE; a.add_row = nullptr; a.frame_row = nullptr; a.resid = nullptr;
       a.out_f32 = scratch; a.ldo = 256; a.out_act = nullptr; a.out_ln = nullptr;
-      launch_gemm_simt<TA>(a, st);
+      gemm_plain<TA>(a, st);
       LnArgs l;
       l.x = scratch; l.ldx = 256;
       l.gamma = g.ln1_gamma; l.beta = g.ln1_beta;
@@ -73,7 +82,7 @@ struct Engine {
       a.ln2_gamma = a.ln2_beta = nullptr;
       a.out_ln = nullptr;
       JV_REQUIRE(g.out_f32 != nullptr, JV_ERR_INVALID, "LN2 needs the fp32 output");
-      launch_gemm_simt<TA>(a, st);
+      gemm_plain<TA>(a, st);
     }
     if (g.ln2_gamma) {
       LnArgs l;

@@ -72,6 +72,7 @@ static PackedW make_packed(jv_estimator* h, std::vector<float>&& w, const float*
   p.K_tap = K_tap;
   p.n_taps = n_taps;
   p.W = h->mem.upload_act(w, h->eng.is_bf16());
+  if (!h->eng.is_bf16()) h->mem.upload_tf32_split(w, &p.W_hi, &p.W_lo);
   p.bias = bias ? h->mem.upload_f32(pad_vec(bias, N, N)) : nullptr;
   return p;
 }
@@ -262,6 +263,8 @@ static GemmDesc conv_desc(const FwdCtx& c, const PackedW& w, const void* A0p, co
       g.tap_shift[s * Kw + k] = k - (Kw - 1);  // causal: taps read t-2, t-1, t
     }
   g.W = w.W;
+  g.W_hi = w.W_hi;
+  g.W_lo = w.W_lo;
   g.M = c.M_alloc;
   g.N = w.N;
   g.bias = w.bias;

@@ -84,6 +84,7 @@ static PackedW hpack(jv_hift* h, std::vector<float>&& w, const std::vector<float
   p.K_tap = K_tap;
   p.n_taps = n_taps;
   p.W = h->mem.upload_act(w, h->eng.is_bf16());
+  if (!h->eng.is_bf16()) h->mem.upload_tf32_split(w, &p.W_hi, &p.W_lo);
   p.bias = h->mem.upload_f32(bias);
   return p;
 }
@@ -317,6 +318,8 @@ static GemmDesc hconv_desc(const HCtx& c, const PackedW& w, const void* A, int l
     g.tap_shift[k] = k * dilation - pad;
   }
   g.W = w.W;
+  g.W_hi = w.W_hi;
+  g.W_lo = w.W_lo;
   g.M = c.L.rows[level];
   g.N = w.N;
   g.bias = w.bias;
@@ -450,6 +453,8 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
         g.n_taps = 1;
         g.K_tap = wi.K_tap;
         g.W = wi.W;
+        g.W_hi = wi.W_hi;
+        g.W_lo = wi.W_lo;
       } else {
         g.A[0] = c.b.SST;
         g.lda[0] = 18;
@@ -462,6 +467,8 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
           g.tap_shift[t] = t - su / 2;
         }
         g.W = w.W;
+        g.W_hi = w.W_hi;
+        g.W_lo = w.W_lo;
       }
       g.M = c.L.rows[lv_out];
       g.N = Cn;
@@ -492,6 +499,8 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
         g.tap_shift[t] = P.shifts[t];
       }
       g.W = P.w.W;
+      g.W_hi = P.w.W_hi;
+      g.W_lo = P.w.W_lo;
       g.M = c.L.rows[lv_in];
       g.N = Cn;
       g.bias = P.w.bias;

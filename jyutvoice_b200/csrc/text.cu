@@ -50,6 +50,7 @@ static PackedW te_pack(jv_text* h, std::vector<float>&& w, const std::vector<flo
   p.K_tap = K_tap;
   p.n_taps = n_taps;
   p.W = h->mem.upload_f32(w);
+  h->mem.upload_tf32_split(w, &p.W_hi, &p.W_lo);
   p.bias = h->mem.upload_f32(bias);
   return p;
 }
@@ -236,6 +237,8 @@ static GemmDesc te_desc(const TeCtx& c, const PackedW& w, const float* A, int ld
     g.tap_shift[k] = k - (w.n_taps - 1) / 2;
   }
   g.W = w.W;
+  g.W_hi = w.W_hi;
+  g.W_lo = w.W_lo;
   g.M = c.L.M_alloc;
   g.N = w.N;
   g.bias = w.bias;
@@ -343,6 +346,8 @@ static void te_predict(TeCtx& c, int Tx, const float* x, const float* g_spk, flo
     g.n_taps = 1;
     g.K_tap = TE_C;
     g.W = h->dp_cond.W;
+    g.W_hi = h->dp_cond.W_hi;
+    g.W_lo = h->dp_cond.W_lo;
     g.M = B;
     g.N = TE_H;
     g.bias = h->dp_cond.bias;

@@ -77,6 +77,19 @@ struct DeviceAlloc {
     JV_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
     return p;
   }
+  // 3xTF32 split of an fp32 weight: hi = w with the low 13 mantissa bits cleared (exactly a TF32 number), lo = w - hi
+  void upload_tf32_split(const std::vector<float>& v, float** hi, float** lo) {
+    std::vector<float> h(v.size()), l(v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+      uint32_t u;
+      memcpy(&u, &v[i], 4);
+      u &= 0xffffe000u;
+      memcpy(&h[i], &u, 4);
+      l[i] = v[i] - h[i];
+    }
+    *hi = upload_f32(h);
+    *lo = upload_f32(l);
+  }
   // upload as activation type: fp32 or bf16
   void* upload_act(const std::vector<float>& v, bool as_bf16) {
     if (!as_bf16) return upload_f32(v);
@@ -91,6 +104,8 @@ struct DeviceAlloc {
 // One packed GEMM weight: W[N_pad, n_taps*K_tap] (+ bias[N_pad]); N_pad rows beyond N are zero.
 struct PackedW {
   void* W = nullptr;
+  float* W_hi = nullptr;  // fp32 packs: the 3xTF32 split of W (gemm_tf32.cuh)
+  float* W_lo = nullptr;
   float* bias = nullptr;
   int N = 0, N_pad = 0, K_tap = 0, n_taps = 0;
 };
