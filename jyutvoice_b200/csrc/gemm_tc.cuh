@@ -123,8 +123,14 @@ __device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {  
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+// Remote arrive with release semantics at cluster scope: publishes this thread's prior writes to the peer CTA.  It is a
+// cluster-scope fence: measured (ncu, fused feed-forward) it stalls the warp for several hundred cycles -- use it once per
+// CTA and event, and the relaxed form below where nothing has to be published (e.g. "TMEM drained").
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -424,7 +430,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     }
     for (int i = 0; i < p.n_acc; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, (PAIR ? 2 : 1) * (p.tile_par ? 128 : 32 * N_EPI_WARPS));
+      // PAIR: one elected, relaxed remote arrive per epilogue warp of either CTA (nothing but "TMEM drained" is signalled)
+      mbar_init(tempty_bar + 8 * i, PAIR ? 2 * (p.tile_par ? 4 : N_EPI_WARPS) : (p.tile_par ? 128 : 32 * N_EPI_WARPS));
     }
     for (int i = 0; i < 2 * EPI_WARPS_MAX; ++i) mbar_init(epi_bar + 8 * i, 1);
     mbar_init(wres_bar, 1);
@@ -869,8 +876,12 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         }
       }
       tc_fence_before();
-      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar + 8 * grp, 0));  // the leader's MMA thread waits for both halves
-      else mbar_arrive(tempty_bar + 8 * grp);
+      if constexpr (PAIR) {  // the leader's MMA thread waits for both halves
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(tempty_bar + 8 * grp, 0));
+      } else {
+        mbar_arrive(tempty_bar + 8 * grp);
+      }
       if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait0();  // smem must outlive the last TMA store's reads

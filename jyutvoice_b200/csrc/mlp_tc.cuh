@@ -35,6 +35,7 @@ struct Params {
   const int* frame_row;
   int out_half;  // stream out is fp16 (else bf16: the copy that feeds the next conv)
   int* sat_flag; // fp16 stream: counts stores that reached +-65504 (see GemmDesc::sat_flag)
+  long long* trace;  // debug: per-pair wait-time counters of the MMA thread (jv_debug_attention_trace buffer), or null
 };
 
 __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_constant__ Maps tm, const Params p) {
@@ -362,23 +363,27 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_cons
 // ingests 0.5 MB of weights per tile instead of 1 MB: the single-CTA kernel was bound by exactly that stream (1 MB per
 // tile through L2 -> SM at ~45 B / clk is 23k clk against 16k clk of MMA time).  Everything else (LNX tile, H buffers,
 // accumulators, epilogues) is per CTA as above.  Ring slot = 16 KB: GEMM1 packs two 64-row K blocks into one slot.
-constexpr int PAIR_SMEM_BYTES = SMEM_BYTES;
+constexpr int PAIR_EPI_WARPS = 16;                      // four per TMEM lane quarter: each handles 32 of a hidden chunk's 128 columns
+constexpr int PAIR_THREADS = 128 + 32 * PAIR_EPI_WARPS;  // 640
+constexpr int PAIR_XCH = 4096;                           // LayerNorm statistics exchange: 4 quarters x 4 column shares x 32 lanes x float2
+constexpr int PAIR_OFF_BAR = OFF_XCH + PAIR_XCH;
+constexpr int PAIR_SMEM_BYTES = 1024 + PAIR_OFF_BAR + 512;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fused_pair_kernel(const __grid_constant__ Maps tm, const Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp_fused_pair_kernel(const __grid_constant__ Maps tm, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sA = base + OFF_A, sW = base + OFF_W, sH = base + OFF_H;
   float* vec = reinterpret_cast<float*>(smem_raw + (base + OFF_VEC - raw));
   float* xch_all = reinterpret_cast<float*>(smem_raw + (base + OFF_XCH - raw));
-  const uint32_t bars = base + OFF_BAR;
+  const uint32_t bars = base + PAIR_OFF_BAR;
   const uint32_t a_full = bars, a_empty = bars + 8;
   const uint32_t w_full = bars + 16, w_empty = w_full + 8 * RW;
   const uint32_t acc1_full = w_empty + 8 * RW, acc1_empty = acc1_full + 16;
   const uint32_t h_full = acc1_empty + 16, h_empty = h_full + 16;
   const uint32_t acc2_full = h_empty + 16, acc2_empty = acc2_full + 8;
-  const uint32_t epi_bar = acc2_empty + 8;  // 8 warps x 2 residual-load barriers
-  const uint32_t tmem_slot = epi_bar + 16 * 8;
+  const uint32_t epi_bar = acc2_empty + 8;  // 16 warps x 2 residual-load barriers
+  const uint32_t tmem_slot = epi_bar + 16 * PAIR_EPI_WARPS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -399,13 +404,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc1_full + 8 * i, 1);
-      mbar_init(acc1_empty + 8 * i, 16);
-      mbar_init(h_full + 8 * i, 16);
+      mbar_init(acc1_empty + 8 * i, 2 * PAIR_EPI_WARPS);
+      mbar_init(h_full + 8 * i, PAIR_EPI_WARPS + 1);  // the leader's epilogue warps (local, cheap) + ONE release.cluster arrive of the peer
       mbar_init(h_empty + 8 * i, 1);
     }
     mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 16);
-    for (int i = 0; i < 16; ++i) mbar_init(epi_bar + 8 * i, 1);
+    mbar_init(acc2_empty, 2 * PAIR_EPI_WARPS);
+    for (int i = 0; i < 2 * PAIR_EPI_WARPS; ++i) mbar_init(epi_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -431,7 +436,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
   const int num_pairs = (p.num_tiles + 1) >> 1;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
       // ===================== TMA producer (both CTAs) =====================
       if (lane == 0) {
@@ -474,6 +479,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
     } else if (warp == 1) {
       // ===================== MMA issuer (leader CTA only) =====================
       if (lane == 0 && rank == 0) {
+        // optional trace (jv_debug_attention_trace buffer): cycles the MMA thread spends waiting, per barrier kind
+        long long* tr = p.trace ? p.trace + 8L * (blockIdx.x >> 1) : nullptr;
+        long long w_acc1e = 0, w_wfull = 0, w_hfull = 0, w_acc2e = 0, w_afull = 0;
+        const long long t_begin = tr ? clock64() : 0;
+#define MLP_TWAIT(counter, call)                \
+  do {                                          \
+    const long long c0_ = tr ? clock64() : 0;   \
+    call;                                       \
+    if (tr) counter += clock64() - c0_;         \
+  } while (0)
         const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M 256, N 128
         const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M 256, N 256
         uint32_t wi = 0, t_local = 0;
@@ -481,11 +496,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
         uint32_t uh[2] = {0, 0};
         auto g1 = [&](int c) {
           const int b = c & 1;
-          mbar_wait(acc1_empty + 8 * b, (u1[b] & 1) ^ 1, 33);
+          MLP_TWAIT(w_acc1e, mbar_wait(acc1_empty + 8 * b, (u1[b] & 1) ^ 1, 33));
           tc_fence_after();
           for (int s2 = 0; s2 < 2; ++s2, ++wi) {
             const uint32_t slot = wi % RW;
-            mbar_wait(w_full + 8 * slot, (wi / RW) & 1, 34);
+            MLP_TWAIT(w_wfull, mbar_wait(w_full + 8 * slot, (wi / RW) & 1, 34));
             tc_fence_after();
             for (int kb = 0; kb < 2; ++kb) {
               const uint64_t ad = make_smem_desc(sA + (2 * s2 + kb) * UNIT), bd = make_smem_desc(sW + slot * UNIT + kb * (UNIT / 2));
@@ -499,12 +514,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
         };
         auto g2 = [&](int c) {
           const int b = c & 1;
-          mbar_wait(h_full + 8 * b, uh[b] & 1, 35);
-          if (c == 0) mbar_wait(acc2_empty, (t_local & 1) ^ 1, 36);
+          MLP_TWAIT(w_hfull, mbar_wait(h_full + 8 * b, uh[b] & 1, 35));
+          if (c == 0) MLP_TWAIT(w_acc2e, mbar_wait(acc2_empty, (t_local & 1) ^ 1, 36));
           tc_fence_after();
           for (int kb2 = 0; kb2 < 2; ++kb2, ++wi) {
             const uint32_t slot = wi % RW;
-            mbar_wait(w_full + 8 * slot, (wi / RW) & 1, 37);
+            MLP_TWAIT(w_wfull, mbar_wait(w_full + 8 * slot, (wi / RW) & 1, 37));
             tc_fence_after();
             const uint64_t ad = make_smem_desc(sH + b * 2 * UNIT + kb2 * UNIT), bd = make_smem_desc(sW + slot * UNIT);
 #pragma unroll
@@ -515,7 +530,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
           ++uh[b];
         };
         for (int pt = pair0; pt < num_pairs; pt += pair_step, ++t_local) {
-          mbar_wait(a_full, t_local & 1, 38);
+          MLP_TWAIT(w_afull, mbar_wait(a_full, t_local & 1, 38));
           tc_fence_after();
           g1(0);
           g1(1);
@@ -526,30 +541,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
           }
           umma_commit_cg2(acc2_full, 3);
         }
+        if (tr) {
+          tr[0] = clock64() - t_begin; tr[1] = w_afull; tr[2] = w_wfull; tr[3] = w_acc1e; tr[4] = w_hfull; tr[5] = w_acc2e; tr[6] = t_local;
+        }
+#undef MLP_TWAIT
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    // register pool of the CTA = 640 threads x 96 (the compiled cap): 128 x (96 - 56) freed >= 512 x (104 - 96) requested.
+    // (A larger request blocks in setmaxnreg.inc for ever.)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ===================== epilogue warps (both CTAs, each on its own 128 rows) =====================
+    // 16 warps: quarter q = TMEM lanes, share `sub` (0..3) = 32 of the 128 columns of a hidden chunk and 2 of the 8 output
+    // chunks.  The GELU epilogue of a chunk (tcgen05.ld -> bias -> tanh -> bf16 -> swizzled st.shared) is a latency chain;
+    // with eight warps it took longer than the chunk's MMAs (tensor pipe 30 % busy), sixteen halve it.
     const int e = warp - 4, q = e & 3, sub = e >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t acc1_empty_l = mapa_u32(acc1_empty, 0), h_full_l = mapa_u32(h_full, 0), acc2_empty_l = mapa_u32(acc2_empty, 0);
-    float* xch = xch_all + q * (2 * 32 * 2);
-    auto row_sum2 = [&](float& a, float& b) {  // summed over the two threads that share a row
+    float* xch = xch_all + q * (4 * 32 * 2);
+    auto row_sum2 = [&](float& a, float& b) {  // summed over the four threads that share a row
       xch[(sub * 32 + lane) * 2] = a;
       xch[(sub * 32 + lane) * 2 + 1] = b;
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(64) : "memory");
-      const float ta = xch[lane * 2] + xch[(32 + lane) * 2];
-      const float tb = xch[lane * 2 + 1] + xch[(32 + lane) * 2 + 1];
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(64) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(128) : "memory");
+      float ta = 0.f, tb = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ta += xch[(i * 32 + lane) * 2];
+        tb += xch[(i * 32 + lane) * 2 + 1];
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(128) : "memory");
       a = ta;
       b = tb;
     };
     const float *v_b1 = vec, *v_b2 = vec + HID, *v_g = vec + HID + C, *v_be = vec + HID + 2 * C;
-    const uint32_t sStage = sH + e * 8192;
+    // final-epilogue staging aliases the H buffers (free once acc2 is complete): per warp 4 KB = R0 | R1 (residual in,
+    // 2 x 2 KB... one per output chunk of this warp) -- outputs reuse the residual buffer of the same chunk once it is read
+    const uint32_t sStage = sH + e * 4096;
     const uint32_t ebar = epi_bar + 16 * e;
-    uint32_t ephase = 0, n_out = 0;
     uint32_t u1[2] = {0, 0};
     uint32_t t_local = 0;
     for (int pt = pair0; pt < num_pairs; pt += pair_step, ++t_local) {
@@ -563,52 +592,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
         tc_fence_after();
         mbar_wait(h_empty + 8 * b, (u1[b] & 1) ^ 1, 42);
         ++u1[b];
-        uint32_t a0[32], a1[32];
-        tmem_ld32(tmem_base + lane_addr + b * NC + sub * 64, a0);
-        tmem_ld32(tmem_base + lane_addr + b * NC + sub * 64 + 32, a1);
+        uint32_t a0[32];
+        tmem_ld32(tmem_base + lane_addr + b * NC + sub * 32, a0);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc1_empty_l + 8 * b);
-        const float* bb = v_b1 + c * NC + sub * 64;
-        const uint32_t hk = sH + b * 2 * UNIT + sub * UNIT;
+        if (lane == 0) mbar_arrive_cluster_relaxed(acc1_empty_l + 8 * b);  // "TMEM drained": nothing to publish
+        float v[32];
+        acc_to_f32(a0, v);
+        add_vec32(v, v_b1 + c * NC + sub * 32, 32);
+        act32(v, ACT_GELU, 0.f, nullptr, 32);
+        // this warp's 32 hidden columns: K block (sub >> 1) of H[b], 16-byte chunks (sub & 1) * 4 .. + 3 of the 128-byte row
+        const uint32_t hk = sH + b * 2 * UNIT + (sub >> 1) * UNIT;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(half ? a1[j] : a0[j]) + bb[half * 32 + j];
-          act32(v, ACT_GELU, 0.f, nullptr, 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128u(hk + swz128(row, half * 4 + j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        }
+        for (int j = 0; j < 4; ++j)
+          sts128u(hk + swz128(row, (sub & 1) * 4 + j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                  pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(h_full_l + 8 * b);
+        if (rank == 0) {
+          if (lane == 0) mbar_arrive(h_full + 8 * b);
+        } else {  // the peer publishes its H tile with a single cluster-scope release (it is a fence: several hundred cycles)
+          asm volatile("bar.sync 10, 512;" ::: "memory");
+          if (e == 0 && lane == 0) mbar_arrive_cluster(h_full_l + 8 * b);
+        }
       }
+      // ---- final epilogue: acc2 + b2 + residual -> stream out [-> LayerNorm out]; this warp's chunks: columns (sub + 4 i) * 32
       mbar_wait(acc2_full, t_local & 1, 43);
       tc_fence_after();
       if (lane == 0) {
         mbar_expect_tx(ebar, EPI_B16_BYTES);
         tma_load_2d(&tm.r, ebar, sStage, sub * 32, row0);
         mbar_expect_tx(ebar + 8, EPI_B16_BYTES);
-        tma_load_2d(&tm.r, ebar + 8, sStage + EPI_B16_BYTES, (sub + 2) * 32, row0);
+        tma_load_2d(&tm.r, ebar + 8, sStage + EPI_B16_BYTES, (sub + 4) * 32, row0);
       }
       const uint32_t taddr = tmem_base + lane_addr + 256;
       float sum2 = 0.f, sq2 = 0.f, amax = 0.f;
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int cc = sub + 2 * i, n = cc * 32, ib = i & 1;
+      for (int i = 0; i < 2; ++i) {
+        const int n = (sub + 4 * i) * 32;
+        const uint32_t buf = sStage + i * EPI_B16_BYTES;
         uint32_t acc[32];
         tmem_ld32(taddr + n, acc);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = row_valid ? __uint_as_float(acc[j]) + v_b2[n + j] : 0.f;
-        mbar_wait(ebar + 8 * ib, (ephase >> ib) & 1, 44);
-        ephase ^= 1u << ib;
+        mbar_wait(ebar + 8 * i, t_local & 1, 44);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 r = lds128(sStage + ib * EPI_B16_BYTES + swz64(lane, j));
+          const float4 r = lds128(buf + swz64(lane, j));
           const uint32_t w[4] = {__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z), __float_as_uint(r.w)};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -616,11 +647,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
             v[8 * j + 2 * k] += f.x;
             v[8 * j + 2 * k + 1] += f.y;
           }
-        }
-        __syncwarp();
-        if (lane == 0 && i + 2 < 4) {
-          mbar_expect_tx(ebar + 8 * ib, EPI_B16_BYTES);
-          tma_load_2d(&tm.r, ebar + 8 * ib, sStage + ib * EPI_B16_BYTES, (cc + 4) * 32, row0);
         }
         if (p.gamma) {
 #pragma unroll
@@ -631,27 +657,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
           }
           tmem_st32(taddr + n, acc);
         }
-        const uint32_t hbuf = sStage + (2 + (n_out & 1)) * EPI_B16_BYTES;
-        ++n_out;
-        if (lane == 0) bulk_wait_read1();
-        __syncwarp();
+        __syncwarp();  // every lane has read the residual chunk: the buffer becomes this chunk's output staging
         if (p.out_half) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            sts128u(hbuf + swz64(lane, j), pack_f16_sat(v[8 * j], v[8 * j + 1]), pack_f16_sat(v[8 * j + 2], v[8 * j + 3]),
+            sts128u(buf + swz64(lane, j), pack_f16_sat(v[8 * j], v[8 * j + 1]), pack_f16_sat(v[8 * j + 2], v[8 * j + 3]),
                     pack_f16_sat(v[8 * j + 4], v[8 * j + 5]), pack_f16_sat(v[8 * j + 6], v[8 * j + 7]));
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            sts128u(hbuf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+            sts128u(buf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                     pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tm.o, hbuf, n, row0);
+          tma_store_2d(&tm.o, buf, n, row0);
           bulk_commit();
         }
       }
@@ -661,8 +684,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
         const float mean2 = sum2 * (1.0f / C);
         const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / C) - mean2 * mean2, 0.f) + 1e-5f);
 #pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-          const int n = (sub + 2 * i) * 32;
+        for (int i = 0; i < 2; ++i) {
+          const int n = (sub + 4 * i) * 32;
           uint32_t acc[32];
           tmem_ld32(taddr + n, acc);
           float v[32];
@@ -672,20 +695,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) mlp_fuse
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (lane == 0) bulk_wait_read1();
+          if (lane == 0) {  // buffer i last held the stream-out chunk i: its TMA store must have read it
+            if (i == 0) bulk_wait_read1();
+            else bulk_wait_read1();
+          }
           __syncwarp();
-          stage_store_b16(&tm.l, sStage + (2 + (n_out & 1)) * EPI_B16_BYTES, lane, v, n, row0);
-          ++n_out;
+          stage_store_b16(&tm.l, sStage + i * EPI_B16_BYTES, lane, v, n, row0);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_cluster(acc2_empty_l);
+        mbar_arrive_cluster_relaxed(acc2_empty_l);
         bulk_wait_read0();  // the staging lives in the H buffers: every store has left smem before the next tile writes H
       }
       __syncwarp();
-      asm volatile("bar.sync 9, 256;" ::: "memory");  // ... for all eight epilogue warps
+      asm volatile("bar.sync 9, 512;" ::: "memory");  // ... for all sixteen epilogue warps
     }
     if (lane == 0) bulk_wait0();
   }
@@ -722,7 +747,7 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
     JV_CUDA(cudaFuncSetAttribute(mlp::mlp_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::PAIR_SMEM_BYTES));
   }
   const bool pair = mlp_pair_mode() && num_sms % 2 == 0 && M_alloc / tc::BLOCK_M >= 2;
-  JV_REQUIRE(mlp::SMEM_BYTES <= tc::SMEM_LIMIT, JV_ERR_STATE, "fused MLP: shared memory budget exceeded");
+  JV_REQUIRE(mlp::SMEM_BYTES <= tc::SMEM_LIMIT && mlp::PAIR_SMEM_BYTES <= tc::SMEM_LIMIT, JV_ERR_STATE, "fused MLP: shared memory budget exceeded");
   mlp::Maps tm;
   tm.a = cache.get(lnx_in, 256, M_alloc, 256 * 2, 64, 128, 0);
   tm.w1 = cache.get(W1, 256, 1024, 256 * 2, 64, pair ? 64 : 128, 0);
@@ -740,6 +765,7 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
   p.frame_row = frame_row;
   p.out_half = out_half;
   p.sat_flag = sat_flag;
+  p.trace = attention_trace_buffer();
   ProfileState& ps = profile_state();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ps.on) {
@@ -754,8 +780,8 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
     grid = 2 * std::min((p.num_tiles + 1) / 2, num_sms / 2);  // whole CTA pairs (the kernel carries __cluster_dims__(2,1,1))
   }
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(mlp::THREADS);
-  cfg.dynamicSmemBytes = mlp::SMEM_BYTES;
+  cfg.blockDim = dim3(pair ? mlp::PAIR_THREADS : mlp::THREADS);
+  cfg.dynamicSmemBytes = pair ? mlp::PAIR_SMEM_BYTES : mlp::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute lattr[1];
   lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
