@@ -3,6 +3,8 @@ from .flow_matching import CausalConditionalCFM, CausalConditionalDecoder  # noq
 from .hifigan import HiFTGenerator, ConvRNNF0Predictor  # noqa: F401
 from .text import TextEncoder, DurationPredictor, length_regulate  # noqa: F401
 from .tts import JyutVoiceTTS  # noqa: F401
+from .checkpoint import load_checkpoint, load_hift, load_pretrain, split_flow_checkpoint, write_wav  # noqa: F401
 
 __all__ = ["CausalConditionalCFM", "CausalConditionalDecoder", "HiFTGenerator", "ConvRNNF0Predictor", "TextEncoder",
-           "DurationPredictor", "length_regulate", "JyutVoiceTTS"]
+           "DurationPredictor", "length_regulate", "JyutVoiceTTS", "load_checkpoint", "load_hift", "load_pretrain",
+           "split_flow_checkpoint", "write_wav"]

@@ -18,6 +18,7 @@ import torch.nn as nn
 from torch.nn import functional as F
 
 from .flow_matching import CausalConditionalCFM
+from . import checkpoint as _checkpoint
 from . import text as _text
 
 
@@ -60,7 +61,11 @@ class JyutVoiceTTS(nn.Module):
         self.freeze_decoder = freeze_decoder
         self.freeze_encoder = freeze_encoder
         if pretrain_path:
-            raise NotImplementedError("checkpoint download/loading is outside this path: use load_state_dict")
+            self.load_pretrain(pretrain_path)
+
+    def load_pretrain(self, pretrain_path):
+        """jyutvoice_tts.py:73-105: bare or {"state_dict": ...} checkpoint, strict=False; returns the incompatible keys."""
+        return _checkpoint.load_pretrain(self, pretrain_path)
 
     @torch.inference_mode()
     def synthesise(self, x, x_lengths, lang, tone, word_pos, syllable_pos, spk_embed, prompt_feat=None, prompt_h=None,
