@@ -2,7 +2,7 @@
 //   TextEncoder.forward          jyutvoice/models/text_encoder.py:401-451
 //   DurationPredictor.forward    jyutvoice/models/duration_predictor.py:48-60
 //   durations -> lengths -> hard monotonic alignment -> mu_y gather   jyutvoice/models/jyutvoice_tts.py:184-203
-// fp32 throughout (FFMA GEMM-with-taps engine + the small kernels of text_kernels.cuh): the durations pass through ceil(),
+// fp32 throughout (3xTF32 tcgen05 GEMM-with-taps engine + the small kernels of text_kernels.cuh): the durations pass through ceil(),
 // so this part keeps the reference's arithmetic type in both precision modes.
 #include <cmath>
 #include <memory>

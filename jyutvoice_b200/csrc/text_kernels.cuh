@@ -1,7 +1,7 @@
 // Kernels of the text front of `synthesise`: TextEncoder, DurationPredictor, length
 // regulation.  Reference: jyutvoice/models/text_encoder.py, duration_predictor.py, jyutvoice_tts.py:184-203.
-// Everything is fp32: the durations go through ceil(), so the encoder runs on the exact-arithmetic (FFMA) engine in both
-// precision modes; it is ~0.2 % of the step's FLOPs.
+// Everything is fp32: the durations go through ceil(), so the encoder runs on the fp32-accurate engine (3xTF32 tcgen05,
+// gemm_tf32.cuh; FFMA only for shapes it does not take) in both precision modes; it is ~0.2 % of the step's FLOPs.
 // Layout: utterance b owns token rows [off_b, off_b + Tx_b) followed by TE_GAP zero rows (the k = 5 / k = 3 "same" convs
 // of the prenet / FFN / duration predictor read them as their zero padding); frame_row[m] = b or -1.
 #pragma once
