@@ -173,6 +173,28 @@ int jv_length_durations(int B, int Tx, const int32_t* x_lens_dev, const float* l
 int jv_length_align(int B, int Tx, int Ty, const int32_t* x_lens_dev, const int64_t* y_lengths, const float* cum,
                     const float* mu_x, float* mu_y, int32_t* frame_token, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Speech-token encoder that produces `prompt_h` for voice cloning, batched over ragged
+ * utterances, every utterance computed as the reference's batch-1 call computes it:
+ *   FlowEncoder.forward (infer.py:66-82): embedding(clamp(token, 0)) * mask -> encoder -> Linear(512, 80)
+ *   UpsampleConformerEncoder.forward (jyutvoice/transformer/upsample_encoder.py:290-355) with the hyper-parameters of
+ *   infer.py:44-60: 512 channels, 8 heads, 2048 FFN units, rel-pos attention (transformer/attention.py:196-330),
+ *   pre-lookahead conv, 6 layers, x2 upsampling conv, 4 layers, after_norm.
+ * Keys are those of flow_encoder.pt: `input_embedding.weight` (optional), `encoder.*`, `encoder_proj.*` (optional).  fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct jv_flowenc jv_flowenc;
+int jv_flowenc_create(int device, jv_flowenc** out);
+void jv_flowenc_destroy(jv_flowenc* h);
+int jv_flowenc_set_weight(jv_flowenc* h, const char* key, const float* data, const int64_t* shape, int ndim);
+int jv_flowenc_finalize(jv_flowenc* h);
+size_t jv_flowenc_workspace_bytes(const jv_flowenc* h, int B, int T, const int32_t* lens_host);
+/* Exactly one of `token` ([B, T] int64, device; needs input_embedding) and `xs` ([B, T, 512] fp32, device: the encoder called
+ * on features, upsample_encoder.py:290).  chunk = 0: full context (streaming=False); chunk > 0: the static chunk mask of
+ * streaming=True (utils/mask.py:161-200; the reference uses static_chunk_size = 25, doubled after the upsampling).
+ * out_hidden [B, 2T, 512] (after_norm output) and / or out_h [B, 2T, 80] (needs encoder_proj); rows >= 2 * lens[b] are 0. */
+int jv_flowenc_encode(jv_flowenc* h, int B, int T, const int32_t* lens_host, const int64_t* token, const float* xs, int chunk,
+                      float* out_hidden, float* out_h, void* ws, size_t ws_bytes, void* stream);
+
 /* Profiling of the dominant kernel (the tcgen05 GEMM): between begin and end every launch of it is
  * bracketed by CUDA events on its own stream.  end() synchronises the device and returns the summed
  * kernel time, the summed algorithmic FLOPs (valid frames only) and the launch count. */

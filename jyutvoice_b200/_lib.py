@@ -63,6 +63,13 @@ SIGNATURES = {
     "jv_text_durations": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "jv_length_durations": (c_int, [c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "jv_length_align": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "jv_flowenc_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    "jv_flowenc_destroy": (None, [c_void_p]),
+    "jv_flowenc_set_weight": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, P_i64, c_int]),
+    "jv_flowenc_finalize": (c_int, [c_void_p]),
+    "jv_flowenc_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, P_i32]),
+    "jv_flowenc_encode": (c_int, [c_void_p, c_int, c_int, P_i32, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
     "jv_profile_begin": (c_int, []),
     "jv_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "jv_bench_gemm": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_double)]),

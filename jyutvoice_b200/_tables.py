@@ -156,6 +156,39 @@ def duration_predictor_table(prefix=""):
     return [(prefix + k, s_, kind) for k, s_, kind in t]
 
 
+def flow_encoder_table(vocab_size=6561, prefix=""):
+    """state_dict of the speech-token encoder that produces `prompt_h` (flow_encoder.pt): infer.py:35-64 `FlowEncoder` =
+    input_embedding + UpsampleConformerEncoder (jyutvoice/transformer/upsample_encoder.py:140-288 with 512 channels, 8 heads,
+    2048 FFN units, 6 + 4 rel-pos layers, no macaron / cnn module) + encoder_proj.  kind adds: pb (pos_bias_u / v, xavier)."""
+    C, Fc = 512, 2048
+    t = [("input_embedding.weight", (vocab_size, C), "emb")]
+    e = "encoder."
+    for emb in ("embed", "up_embed"):
+        t += [(f"{e}{emb}.out.0.weight", (C, C), "w"), (f"{e}{emb}.out.0.bias", (C,), "b"),
+              (f"{e}{emb}.out.1.weight", (C,), "g"), (f"{e}{emb}.out.1.bias", (C,), "beta")]
+    t += [(e + "after_norm.weight", (C,), "g"), (e + "after_norm.bias", (C,), "beta"),
+          (e + "pre_lookahead_layer.conv1.weight", (C, C, 4), "w"), (e + "pre_lookahead_layer.conv1.bias", (C,), "b"),
+          (e + "pre_lookahead_layer.conv2.weight", (C, C, 3), "w"), (e + "pre_lookahead_layer.conv2.bias", (C,), "b"),
+          (e + "up_layer.conv.weight", (C, C, 5), "w"), (e + "up_layer.conv.bias", (C,), "b")]
+    for stack, n in (("encoders", 6), ("up_encoders", 4)):
+        for i in range(n):
+            a = f"{e}{stack}.{i}."
+            t += [(a + "self_attn.pos_bias_u", (8, 64), "pb"), (a + "self_attn.pos_bias_v", (8, 64), "pb")]
+            for lin in ("q", "k", "v", "out"):
+                t += [(a + f"self_attn.linear_{lin}.weight", (C, C), "w"), (a + f"self_attn.linear_{lin}.bias", (C,), "b")]
+            t += [(a + "self_attn.linear_pos.weight", (C, C), "w"),
+                  (a + "feed_forward.w_1.weight", (Fc, C), "w"), (a + "feed_forward.w_1.bias", (Fc,), "b"),
+                  (a + "feed_forward.w_2.weight", (C, Fc), "w"), (a + "feed_forward.w_2.bias", (C,), "b"),
+                  (a + "norm_ff.weight", (C,), "g"), (a + "norm_ff.bias", (C,), "beta"),
+                  (a + "norm_mha.weight", (C,), "g"), (a + "norm_mha.bias", (C,), "beta")]
+    t += [("encoder_proj.weight", (80, C), "w"), ("encoder_proj.bias", (80,), "b")]
+    return [(prefix + k, s_, kind) for k, s_, kind in t]
+
+
+def flow_encoder_keys(vocab_size=6561):
+    return [(k, tuple(s_)) for k, s_, _ in flow_encoder_table(vocab_size)]
+
+
 def text_encoder_keys(n_vocab=97, n_lang=4, n_tone=7):
     return [(k, tuple(s_)) for k, s_, _ in text_encoder_table(n_vocab, n_lang, n_tone)]
 

@@ -541,7 +541,7 @@ static void run_decode(const HCtx& c, const float* mel, const float* s, float* w
     e.gemm(g, c.st);
   }
   dim3 grid(cdiv(480 * c.Tmax, 1024), c.L.B);
-  hift_istft_kernel<<<grid, 256, 0, c.st>>>(c.b.SPEC, SPEC_LD, c.sq, c.Tmax, wav, h->istft_tb, 0.99f, (long)c.L.rows_alloc[3]);
+  hift_istft_kernel<<<grid, ISTFT_THREADS, 0, c.st>>>(c.b.SPEC, SPEC_LD, c.sq, c.Tmax, wav, h->istft_tb, 0.99f, (long)c.L.rows_alloc[3]);
   JV_LAUNCHED();
 }
 

@@ -320,13 +320,16 @@ struct IstftTables {
   float w2[16];
 };
 
-// One block = 1024 output samples of one utterance = 256 hops (+ 3 frames of overlap).  Phase 1, one thread per frame:
+constexpr int ISTFT_THREADS = 288;
+// One block = 1024 output samples of one utterance = 256 hops (+ 3 frames of overlap) = 259 frames: 288 threads, so that
+// phase 1 is ONE round of loads (with 256 threads the 3 overlap frames cost a second, nearly empty, latency round).
+// Phase 1, one thread per frame:
 // read the frame's 18 values (rows are `ld` = SPEC_LD floats apart: 16-byte loads), magnitude / phase with three MUFU ops
 // per bin (ex2, sin, cos .approx after an exact range reduction; libm's expf / sinf / sincosf bound the old kernel), then the
 // windowed 16-point inverse DFT as FFMAs whose table operands come straight from the constant bank, and the 16 samples
 // go to shared memory.  Phase 2, four samples per thread: overlap-add of the four frames that cover a sample, envelope,
 // clamp, one 16-byte store.
-__global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict__ SPEC, int ld, HiftSeq sq, int Tmax,
+__global__ void __launch_bounds__(ISTFT_THREADS) hift_istft_kernel(const float* __restrict__ SPEC, int ld, HiftSeq sq, int Tmax,
                                                          float* __restrict__ wav, const IstftTables tb, float limit, long spec_rows) {
   constexpr int NF = 259;             // frames a block touches: f_lo .. f_lo + 258
   __shared__ float Y[16][NF + 1];     // Y[j][frame]: sample j of the frame's windowed inverse DFT (conflict-free in both phases)
@@ -337,14 +340,15 @@ __global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict
   if (n0 >= 480 * Tmax) return;
   float4* out = reinterpret_cast<float4*>(wav + (long)b * Lmax + n0) + threadIdx.x;
   const int n = n0 + 4 * threadIdx.x;
+  const bool writer = threadIdx.x < 256;
   if (n0 >= 480 * T) {  // block entirely beyond the utterance
-    if (n < 480 * Tmax) *out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (writer && n < 480 * Tmax) *out = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
   const int F = 120 * T + 1;
   const int f_lo = n0 / 4 - 1;        // sample n is covered by frames (n + 8) / 4 - 3 .. (n + 8) / 4
   const long row0 = 120L * sq.off[b];
-  for (int fi = threadIdx.x; fi < NF; fi += 256) {
+  if (const int fi = threadIdx.x; fi < NF) {
     const int f = f_lo + fi;
     float y[16];
     if (f >= 0 && f < F && row0 + f < spec_rows) {
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(256) hift_istft_kernel(const float* __restrict
     for (int j = 0; j < 16; ++j) Y[j][fi] = y[j];
   }
   __syncthreads();
-  if (n >= 480 * Tmax) return;
+  if (!writer || n >= 480 * Tmax) return;
   float r[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

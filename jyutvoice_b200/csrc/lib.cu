@@ -4,3 +4,4 @@
 #include "estimator.cu"
 #include "hift.cu"
 #include "text.cu"
+#include "flowenc.cu"

@@ -19,7 +19,8 @@ import math
 
 import torch
 
-from ._tables import estimator_table, hift_table, text_encoder_table, duration_predictor_table  # noqa: F401  (the single key/shape tables)
+from ._tables import (estimator_table, hift_table, text_encoder_table, duration_predictor_table,  # noqa: F401  (the single key/shape tables)
+                      flow_encoder_table)
 
 
 def _bias_shape(table, idx):
@@ -50,6 +51,8 @@ def _draw(table, seed, w_gain=math.sqrt(3.0), g_range=(0.8, 1.2), alpha_range=(0
             sd[key] = 0.05 * torch.randn(shape, generator=g)
         elif kind == "emb":
             sd[key] = torch.randn(shape, generator=g) * shape[1] ** -0.5
+        elif kind == "pb":  # xavier_uniform_ over [heads, d_k] (attention.py:222-223)
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * math.sqrt(6.0 / (shape[0] + shape[1]))
         elif kind == "alpha":
             sd[key] = alpha_range[0] + (alpha_range[1] - alpha_range[0]) * torch.rand(shape, generator=g)
         elif kind == "wn_g":
@@ -134,6 +137,14 @@ def make_duration_predictor_state_dict(seed=1357):
     sd = _draw(duration_predictor_table(), seed, w_gain=1.0)
     sd["proj.weight"] = sd["proj.weight"] * 0.15
     sd["proj.bias"] = torch.full((1,), 0.35)
+    return sd
+
+
+def make_flow_encoder_state_dict(seed=9753, vocab_size=6561):
+    """Speech-token encoder weights under the keys of flow_encoder.pt (infer.py:35-64, upsample_encoder.py:140-288).
+    The token embedding is drawn N(0, 1) like nn.Embedding's default."""
+    sd = _draw(flow_encoder_table(vocab_size), seed, w_gain=1.0)
+    sd["input_embedding.weight"] = sd["input_embedding.weight"] * math.sqrt(512.0)
     return sd
 
 

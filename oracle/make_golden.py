@@ -97,6 +97,31 @@ def synth_golden():
         print(name, "T =", int(out["mel_lengths"][0]))
 
 
+def flow_encoder_tokens(seed, T):
+    return torch.randint(0, 6561, (1, T), generator=torch.Generator().manual_seed(seed))
+
+
+def flow_encoder_golden():
+    """The reference's speech-token encoder (infer.py:35-82 FlowEncoder = input_embedding + UpsampleConformerEncoder +
+    encoder_proj) on two prompts: full context, and the encoder's static chunk mask (streaming=True)."""
+    m = ref_shims.build_reference_flow_encoder()
+    from jyutvoice.utils.mask import make_pad_mask
+    sd = weights.make_flow_encoder_state_dict()
+    m.load_state_dict(sd, strict=True)
+    out = {"weights_checksum": np.float64(sum(float(v.double().abs().sum()) for v in sd.values())), "n_cases": 2}
+    for ci, (seed, T, streaming) in enumerate(((41, 37, False), (43, 61, True))):
+        token = flow_encoder_tokens(seed, T)
+        token_len = torch.tensor([T])
+        with torch.no_grad():   # infer.py:77-82 verbatim
+            mask = (~make_pad_mask(token_len)).float().unsqueeze(-1)
+            x = m.input_embedding(torch.clamp(token, min=0)) * mask
+            hid, masks = m.encoder(x, token_len, streaming=streaming)
+            h = m.encoder_proj(hid)
+        out.update({f"c{ci}_seed": seed, f"c{ci}_T": T, f"c{ci}_streaming": int(streaming), f"c{ci}_h": h.numpy(),
+                    f"c{ci}_hidden": hid.numpy(), f"c{ci}_masks": masks.numpy()})
+    np.savez_compressed(os.path.join(OUT, "flow_encoder.npz"), **out)
+
+
 def module_inputs(seed):
     """Inputs of the per-module fixtures: a ragged 3-row batch of 45 frames."""
     g = torch.Generator().manual_seed(seed)
@@ -234,6 +259,8 @@ def main():
     module_golden()
     # ---------------- end to end: the reference's JyutVoiceTTS.synthesise (config 1 of BASELINE.json) ----------------
     synth_golden()
+    # ---------------- speech-token encoder (prompt_h) ----------------
+    flow_encoder_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

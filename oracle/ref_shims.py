@@ -220,3 +220,24 @@ def build_reference_tts(cfm=None):
     tts = JyutVoiceTTS(encoder=encoder, decoder=cfm if cfm is not None else build_reference_cfm(), dp=dp, output_size=80,
                        spk_embed_dim=192)
     return tts.eval()
+
+
+def build_reference_flow_encoder():
+    """The reference's speech-token encoder: UpsampleConformerEncoder with the hyper-parameters of infer.py:44-60, plus the
+    two layers infer.py's FlowEncoder wraps around it (input_embedding 6561 x 512, encoder_proj 512 -> 80), as a plain
+    container with the same state_dict keys as flow_encoder.pt.  Random init."""
+    install()
+    from jyutvoice.transformer.upsample_encoder import UpsampleConformerEncoder
+
+    class _FlowEncoder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.input_embedding = nn.Embedding(6561, 512)
+            self.encoder = UpsampleConformerEncoder(
+                output_size=512, attention_heads=8, linear_units=2048, num_blocks=6, dropout_rate=0.1,
+                positional_dropout_rate=0.1, attention_dropout_rate=0.1, normalize_before=True, input_layer="linear",
+                pos_enc_layer_type="rel_pos_espnet", selfattention_layer_type="rel_selfattn", input_size=512,
+                use_cnn_module=False, macaron_style=False, static_chunk_size=25)
+            self.encoder_proj = nn.Linear(512, 80)
+
+    return _FlowEncoder().eval()

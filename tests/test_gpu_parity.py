@@ -757,3 +757,96 @@ def test_synthesise_from_tokens_golden(name, precision, text_front, est_sd):
     ref = torch.from_numpy(g["decoder_outputs"])
     err = (out["decoder_outputs"].cpu() - ref).abs().max().item()
     assert err <= (FP32_MEL_TOL if precision == "fp32" else BF16_MEL_TOL), err
+
+
+# ------------------------------------------------------------------------------ speech-token encoder
+@pytest.fixture(scope="module")
+def flow_encoder():
+    from jyutvoice_b200 import FlowEncoder, synthetic
+    enc = FlowEncoder()
+    enc.load_state_dict(synthetic.make_flow_encoder_state_dict(), strict=True)
+    return enc.cuda()
+
+
+FLOWENC_TOL = 2e-4   # fp32 (3xTF32 contractions, 10 layers, |hidden| ~ 5): measured ~2e-5
+
+
+def test_flow_encoder_golden_gpu(flow_encoder):
+    """Token ids -> prompt_h against the reference's own FlowEncoder outputs: full context and the static chunk mask."""
+    from oracle.make_golden import flow_encoder_tokens
+    g = np.load(os.path.join(GOLDEN, "flow_encoder.npz"))
+    for ci in range(int(g["n_cases"])):
+        T = int(g[f"c{ci}_T"])
+        token = flow_encoder_tokens(int(g[f"c{ci}_seed"]), T).cuda()
+        h, masks = flow_encoder(token, torch.tensor([T]).cuda(), streaming=bool(g[f"c{ci}_streaming"]))
+        assert h.shape == (1, 2 * T, 80) and np.array_equal(masks.cpu().numpy(), g[f"c{ci}_masks"])
+        err = (h.cpu() - torch.from_numpy(g[f"c{ci}_h"])).abs().max().item()
+        assert err <= FLOWENC_TOL, (ci, err)
+
+
+def test_flow_encoder_ragged_batch_vs_oracle(flow_encoder):
+    """A ragged batch (the reference's call site is batch 1) against the oracle utterance by utterance, including a 1-token
+    prompt, negative (clamped) ids, and exact zeros beyond each utterance; the encoder-only module on features gives the
+    same hidden states as the token path."""
+    from jyutvoice_b200 import UpsampleConformerEncoder, synthetic
+    from oracle import flow_encoder as ofe
+    sd = synthetic.make_flow_encoder_state_dict()
+    g = torch.Generator().manual_seed(7)
+    lens = [75, 1, 40, 66]
+    B, T = len(lens), max(lens)
+    token = torch.randint(0, 6561, (B, T), generator=g)
+    token[2, 3] = -1
+    for streaming in (False, True):
+        h, masks = flow_encoder(token.cuda(), torch.tensor(lens).cuda(), streaming=streaming)
+        h = h.cpu()
+        for b, l in enumerate(lens):
+            with torch.no_grad():
+                ref, _ = ofe.flow_encoder_forward(sd, token[b:b + 1, :l], streaming)
+            err = (h[b:b + 1, : 2 * l] - ref).abs().max().item()
+            assert err <= FLOWENC_TOL, (streaming, b, err)
+            assert float(h[b, 2 * l:].abs().max()) == 0.0 if 2 * l < 2 * T else True
+            assert int(masks[b].sum()) == 2 * l
+    enc = UpsampleConformerEncoder()
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    enc = enc.cuda()
+    xs = sd["input_embedding.weight"][token.clamp(min=0)].cuda()
+    hid, masks2 = enc(xs, torch.tensor(lens).cuda())
+    for b, l in enumerate(lens):
+        with torch.no_grad():
+            _, ref_hid = ofe.flow_encoder_forward(sd, token[b:b + 1, :l], False)
+        assert (hid[b:b + 1, : 2 * l].cpu() - ref_hid).abs().max().item() <= FLOWENC_TOL
+    assert torch.equal(masks2, masks)
+
+
+def test_flow_encoder_errors(flow_encoder):
+    from jyutvoice_b200 import UpsampleConformerEncoder
+    with pytest.raises(ValueError):
+        flow_encoder(torch.zeros(2, 5, dtype=torch.long).cuda(), torch.tensor([5, 6]).cuda())      # length beyond T
+    with pytest.raises(RuntimeError):
+        flow_encoder.cpu()(torch.zeros(1, 5, dtype=torch.long), torch.tensor([5]))                 # no CPU path
+    flow_encoder.cuda()
+    with pytest.raises(ValueError):
+        UpsampleConformerEncoder(macaron_style=True)
+    enc = UpsampleConformerEncoder().cuda()                                                        # zero weights: still runs
+    out, _ = enc(torch.zeros(1, 3, 512).cuda(), torch.tensor([3]).cuda())
+    assert torch.isfinite(out).all()
+
+
+def test_prompt_h_from_tokens_feeds_synthesise(flow_encoder, text_front, est_sd):
+    """The voice-cloning call sequence of infer.py:386-432 on the GPU: speech tokens -> FlowEncoder -> prompt_h -> synthesise;
+    the generated part has the regulated length and the result is finite."""
+    from jyutvoice_b200 import JyutVoiceTTS, CausalConditionalCFM, CausalConditionalDecoder, synthetic
+    from oracle.make_golden import synth_inputs
+    enc, dp = text_front
+    cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision="bf16"))
+    cfm.load_state_dict(est_sd, strict=True)
+    tts = JyutVoiceTTS(encoder=enc, decoder=cfm, dp=dp)
+    tts.spk_embed_affine_layer.load_state_dict(synthetic.make_spk_affine_state_dict())
+    tts = tts.cuda()
+    Tp = 30
+    token = torch.randint(0, 6561, (1, Tp), generator=torch.Generator().manual_seed(2)).cuda()
+    prompt_h, _ = flow_encoder(token, torch.tensor([Tp]).cuda())
+    prompt_feat = torch.randn(1, 2 * Tp, 80, generator=torch.Generator().manual_seed(3)).cuda()
+    inp = [z.cuda() for z in synth_inputs(11, 20)]
+    out = tts.synthesise(*inp, prompt_feat=prompt_feat, prompt_h=prompt_h, n_timesteps=4)
+    assert out["decoder_outputs"].shape[-1] == int(out["mel_lengths"][0]) and torch.isfinite(out["decoder_outputs"]).all()

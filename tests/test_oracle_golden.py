@@ -160,3 +160,19 @@ def test_text_front_golden(name):
     assert np.array_equal(y_len.numpy(), g["mel_lengths"])
     assert np.array_equal(attn.numpy().astype(np.uint8), g["attn"])
     assert (mu_y - torch.from_numpy(g["encoder_outputs"])).abs().max().item() <= 1e-5
+
+
+def test_flow_encoder_golden():
+    """oracle/flow_encoder.py against the reference's speech-token encoder outputs (synthetic weights): full context and
+    the static chunk mask."""
+    from oracle import flow_encoder as ofe
+    from oracle.make_golden import flow_encoder_tokens
+    g = np.load(os.path.join(GOLDEN, "flow_encoder.npz"))
+    sd = weights.make_flow_encoder_state_dict()
+    assert abs(sum(float(v.double().abs().sum()) for v in sd.values()) - float(g["weights_checksum"])) <= 1e-6 * float(g["weights_checksum"])
+    for ci in range(int(g["n_cases"])):
+        token = flow_encoder_tokens(int(g[f"c{ci}_seed"]), int(g[f"c{ci}_T"]))
+        with torch.no_grad():
+            h, hid = ofe.flow_encoder_forward(sd, token, bool(g[f"c{ci}_streaming"]))
+        assert (hid - torch.from_numpy(g[f"c{ci}_hidden"])).abs().max().item() <= 1e-5
+        assert (h - torch.from_numpy(g[f"c{ci}_h"])).abs().max().item() <= 1e-5

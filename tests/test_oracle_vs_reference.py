@@ -43,3 +43,26 @@ def test_hift_matches_reference(hift_sd):
         wav_m, s_m = oh.inference(hift_sd, mel, rng)
     assert (s_r - s_m).abs().max().item() <= 1e-6
     assert snr_db(wav_r, wav_m) >= 90.0
+
+
+def test_flow_encoder_matches_reference():
+    """oracle/flow_encoder.py against the reference's UpsampleConformerEncoder (+ the two layers of infer.py's FlowEncoder):
+    the synthetic weights load strict, and outputs agree for a 1-token prompt, full context and the static chunk mask."""
+    from oracle import flow_encoder as ofe
+    m = ref_shims.build_reference_flow_encoder()
+    sd = weights.make_flow_encoder_state_dict()
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    from jyutvoice.utils.mask import make_pad_mask
+    g = torch.Generator().manual_seed(1)
+    for T, streaming in ((1, False), (29, False), (58, True)):
+        token = torch.randint(0, 6561, (1, T), generator=g)
+        tl = torch.tensor([T])
+        with torch.no_grad():
+            x = m.input_embedding(torch.clamp(token, min=0)) * (~make_pad_mask(tl)).float().unsqueeze(-1)
+            hid, masks = m.encoder(x, tl, streaming=streaming)
+            h = m.encoder_proj(hid)
+            mine_h, mine_hid = ofe.flow_encoder_forward(sd, token, streaming)
+        assert masks.shape == (1, 1, 2 * T) and bool(masks.all())
+        assert (hid - mine_hid).abs().max().item() <= 1e-5
+        assert (h - mine_h).abs().max().item() <= 1e-5
