@@ -481,7 +481,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
       if (lane == 0 && rank == 0) {
         // optional trace (jv_debug_attention_trace buffer): cycles the MMA thread spends waiting, per barrier kind
         long long* tr = p.trace ? p.trace + 8L * (blockIdx.x >> 1) : nullptr;
-        long long w_acc1e = 0, w_wfull = 0, w_hfull = 0, w_acc2e = 0, w_afull = 0;
+        long long w_acc1e = 0, w_wfull = 0, w_hfull = 0, w_acc2e = 0, w_afull = 0, t_g1 = 0;  // t_g1: all of g1 incl. its waits
         const long long t_begin = tr ? clock64() : 0;
 #define MLP_TWAIT(counter, call)                \
   do {                                          \
@@ -496,6 +496,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
         uint32_t uh[2] = {0, 0};
         auto g1 = [&](int c) {
           const int b = c & 1;
+          const long long g1_0 = tr ? clock64() : 0, g1_w0 = w_acc1e + w_wfull;
           MLP_TWAIT(w_acc1e, mbar_wait(acc1_empty + 8 * b, (u1[b] & 1) ^ 1, 33));
           tc_fence_after();
           for (int s2 = 0; s2 < 2; ++s2, ++wi) {
@@ -511,6 +512,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
           }
           umma_commit_cg2(acc1_full + 8 * b, 3);
           ++u1[b];
+          if (tr) t_g1 += (clock64() - g1_0) - (w_acc1e + w_wfull - g1_w0);  // issue time of the 16 MMAs + 3 commits, waits excluded
         };
         auto g2 = [&](int c) {
           const int b = c & 1;
@@ -542,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
           umma_commit_cg2(acc2_full, 3);
         }
         if (tr) {
-          tr[0] = clock64() - t_begin; tr[1] = w_afull; tr[2] = w_wfull; tr[3] = w_acc1e; tr[4] = w_hfull; tr[5] = w_acc2e; tr[6] = t_local;
+          tr[0] = clock64() - t_begin; tr[1] = w_afull; tr[2] = w_wfull; tr[3] = w_acc1e; tr[4] = w_hfull; tr[5] = w_acc2e; tr[6] = t_local; tr[7] = t_g1;
         }
 #undef MLP_TWAIT
       }

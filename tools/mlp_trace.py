@@ -23,7 +23,10 @@ cfm(mu, None, 1, 1.0, spks, None, lengths=[T] * B)
 torch.cuda.synchronize()
 L.jv_debug_attention_trace(ctypes.c_void_p(0))
 t = buf.cpu().view(-1, 8)[:74].double()
-names = ["MMA thread total", "wait LNX tile (a_full)", "wait weights (w_full)", "wait acc1 drained", "wait H written (h_full)", "wait acc2 drained", "tiles"]
+names = ["MMA thread total", "wait LNX tile (a_full)", "wait weights (w_full)", "wait acc1 drained", "wait H written (h_full)", "wait acc2 drained", "tiles", "FF1 issue (16 MMAs x chunks, waits excluded)"]
 for k, n in enumerate(names):
     x = t[:, k]
     print(f"{n:28s} mean {x.mean():9.0f}  p50 {x.median():9.0f}  max {x.max():9.0f}")
+issue = t[:, 0] - t[:, 1:6].sum(1)
+print(f"issue time total             mean {issue.mean():9.0f}   FF1 part {t[:, 7].mean():9.0f}   FF2 part (+ loop) {(issue - t[:, 7]).mean():9.0f}")
+print(f"per MMA: FF1 (N=128) {(t[:, 7] / (t[:, 6] * 128)).mean():6.1f} clk   FF2 (N=256) {((issue - t[:, 7]) / (t[:, 6] * 64)).mean():6.1f} clk")
