@@ -28,6 +28,7 @@ def build(verbose=False):
     ref_shims.build_reference_cfm()
     ref_shims.build_reference_hift()
     ref_shims.build_reference_tts()  # text encoder, duration predictor, JyutVoiceTTS.synthesise
+    ref_shims.build_reference_flow_encoder()  # UpsampleConformerEncoder (prompt_h)
     files = set()
     for name, mod in list(sys.modules.items()):
         f = getattr(mod, "__file__", None)
