@@ -602,6 +602,12 @@ int jv_debug_attention_trace(void* buf) {  // development aid, not part of inclu
   return JV_OK;
 }
 
+int jv_debug_gemm_trace(void* buf, int epi) {  // development aid, not part of include/jyutvoice_b200.h
+  gemm_trace().buf = (long long*)buf;
+  gemm_trace().epi = epi;
+  return JV_OK;
+}
+
 int jv_estimator_set_stream_format(jv_estimator* h, int format) {
   JV_API_BEGIN
   JV_REQUIRE(h && format >= 0 && format <= 2, JV_ERR_INVALID, "format must be 0 (fp16), 1 (bf16) or 2 (fp32)");

@@ -72,6 +72,7 @@ struct KernelEntry {
   int epi;
   KernelFn fn;
   KernelFn fn_pair;  // cta_group::2 variant of the same epilogue
+  KernelFn fn_wln = nullptr, fn_wln_pair = nullptr;  // sixteen-warp sixteen-warp LayerNorm epilogue (16-bit stream kernels)
 };
 constexpr int N_KERNELS = 12;
 // the epilogue shapes the estimator / HiFT graphs actually use, plus the run-time generic kernel (last)
@@ -87,8 +88,10 @@ static const KernelEntry* kernel_table() {
       {EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_RESID | EPI_F32>, gemm_taps_tc_kernel<EPI_RESID | EPI_F32, true>},                        // HiFT ups + source, last conv2
       {EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_F32 | EPI_OACT>, gemm_taps_tc_kernel<EPI_F32 | EPI_OACT, true>},                          // HiFT source_downs (im2col)
       // bf16 residual stream (estimator, bf16 mode)
-      {EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, true>},
-      {EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, true>},
+      {EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, true>,
+       gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, false, true>, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32 | EPI_LN2, true, true>},
+      {EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, true>,
+       gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, false, true>, gemm_taps_tc_kernel<EPI_XB | EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, true, true>},
       {EPI_XB | EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32>, gemm_taps_tc_kernel<EPI_XB | EPI_RESID | EPI_F32, true>},
       {-1, gemm_taps_tc_kernel<-1>, gemm_taps_tc_kernel<-1, true>},
   };
@@ -99,6 +102,16 @@ bool use_pdl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("JYUTVOICE_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// JYUTVOICE_B200_EPI16=0: eight instead of sixteen epilogue warps for the residual + LayerNorm kernels of the 16-bit stream
+static bool use_epi16() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JYUTVOICE_B200_EPI16");
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
@@ -187,6 +200,10 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
     for (int i = 0; i < N_KERNELS; ++i) {
       JV_CUDA(cudaFuncSetAttribute((const void*)kernel_table()[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
       JV_CUDA(cudaFuncSetAttribute((const void*)kernel_table()[i].fn_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+      if (kernel_table()[i].fn_wln) {
+        JV_CUDA(cudaFuncSetAttribute((const void*)kernel_table()[i].fn_wln, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+        JV_CUDA(cudaFuncSetAttribute((const void*)kernel_table()[i].fn_wln_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+      }
     }
   }
   tc::TcParams p;
@@ -230,13 +247,18 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
                ? 1
                : 0;
   if (p.pair) p.b_stage_bytes = round_up((p.block_n / 2) * tc::BLOCK_K * 2, 1024);
-  const bool wide = epi == tc::EPI_OACT;  // bf16-only epilogue: 16 epilogue warps, small staging
+  const bool epi16 = g.x_bf16 && g.resid && g.ln2_gamma && g.N == 256 && p.block_n == 256 && use_epi16();
+  const bool wide = epi == tc::EPI_OACT || epi16;  // 16 epilogue warps, small staging: bf16-only epilogues and the sixteen-warp LayerNorm epilogue
   const int n_epi_warps = wide ? tc::EPI_WARPS_MAX : tc::EPI_WARPS;
   {  // staging layout per epilogue warp, exactly what this epilogue kind needs
     const bool f_resid = epi & tc::EPI_RESID, f_f32 = epi & tc::EPI_F32, f_oact = epi & tc::EPI_OACT;
     int off = 0;
     p.off_R = 0;
-    if (g.x_bf16) {  // R0 R1 | O0 | O1, 2 KB each
+    p.epi16 = epi16 ? 1 : 0;
+    if (p.epi16) {  // sixteen warps: R0 R1 (residual in, stream out, LayerNorm out), 2 KB each
+      p.off_OF = p.off_OB = 0;
+      off = 2 * tc::EPI_B16_BYTES;
+    } else if (g.x_bf16) {  // R0 R1 | O0 | O1, 2 KB each
       p.off_OF = 2 * tc::EPI_B16_BYTES;
       p.off_OB = 3 * tc::EPI_B16_BYTES;
       off = 4 * tc::EPI_B16_BYTES;
@@ -310,6 +332,7 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
     }
     p.debug = dbg;
   }
+  p.trace = (gemm_trace().buf && gemm_trace().epi == epi) ? gemm_trace().buf : nullptr;
   if (cache.maps.size() > 4096) cache.maps.clear();  // before the gets: references must stay valid below
   tc::TcMaps tm;
   tm.a0 = cache.get(g.A[0], g.K_tap, g.a_rows[0], (long)g.lda[0] * 2, tc::BLOCK_K, p.slab ? p.slab_rows : tc::BLOCK_M, 0);
@@ -352,7 +375,8 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
   bool found = false;
   for (int i = 0; i < N_KERNELS - 1; ++i)
     if (kernel_table()[i].epi == epi) { ke = &kernel_table()[i]; found = true; }
-  KernelFn fn = p.pair ? ke->fn_pair : ke->fn;
+  KernelFn fn = p.epi16 ? (p.pair ? ke->fn_wln_pair : ke->fn_wln) : (p.pair ? ke->fn_pair : ke->fn);
+  JV_REQUIRE(fn != nullptr, JV_ERR_STATE, "no kernel for epilogue kind %d", epi);
   JV_REQUIRE(found || !g.x_bf16, JV_ERR_INVALID, "no bf16-stream kernel for epilogue kind %d", epi);
   JV_CUDA(cudaLaunchKernelEx(&cfg, fn, tm, g, p));
   JV_LAUNCHED();

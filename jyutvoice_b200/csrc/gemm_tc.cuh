@@ -35,7 +35,7 @@ constexpr int EPI_BYTES_PER_WARP = 2 * EPI_F32_BYTES + EPI_B16_BYTES;  // residu
 constexpr int BAR_BYTES = 640;   // mbarriers
 constexpr int MAX_ACC = 8;       // accumulator stages in TMEM (512 columns / block_n, at most 8)
 constexpr int TAB_BYTES = 1024;  // slab mode: a_off[32] + b_desc[<=96] (uint64)
-constexpr int XCH_BYTES = 2048;  // row-statistics exchange of LayerNorm epilogues: 4 quarters x 2 warps x 32 lanes x float2
+constexpr int XCH_BYTES = 4096;  // row-statistics exchange of LayerNorm epilogues: 4 quarters x (2 or 4) warps x 32 lanes x float2
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_THREADS = 384;
@@ -149,6 +149,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read4() { asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -197,6 +198,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// issue only: several loads in flight, one tmem_ld_wait() for all of them
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -327,6 +341,9 @@ struct TcParams {
   // so every uncached read of bias / gamma / beta / alpha is an L2 round trip inside the epilogue's dependency chain.
   int vec_bias, vec_ln1, vec_ln2, vec_act, vec_act2;
   int debug;               // experiments only (JYUTVOICE_B200_DEBUG): 1 = no output stores, 2 = no epilogue at all
+  int epi16;               // XB + residual + LN2 kernels with N == block_n == 256: the sixteen-warp epilogue (WLN instantiations)
+  long long* trace;        // debug (tools/gemm_trace.py): per-CTA clock64 sums, 8 slots per CTA: MMA thread total | wait tempty |
+                           // wait full | units ; epilogue warp 0: total | wait tfull | wait residual | -
 };
 
 // byte offset of 16-byte chunk j of row r inside a staging buffer
@@ -379,8 +396,8 @@ constexpr int EPI_XB = 32;
 
 // PAIR: the cta_group::2 variant (TcParams::pair).  A separate instantiation, not a run-time switch: a kernel that contains
 // cta_group::2 instructions can only be launched with an even cluster size ("cluster misconfiguration" otherwise).
-template <int EPI, bool PAIR = false>
-__global__ void __launch_bounds__(EPI == EPI_OACT ? NUM_THREADS_WIDE : NUM_THREADS, 1)
+template <int EPI, bool PAIR = false, bool WLN = false>
+__global__ void __launch_bounds__((EPI == EPI_OACT || WLN) ? NUM_THREADS_WIDE : NUM_THREADS, 1)
 gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const TcParams p) {
   const bool F_LN1 = EPI >= 0 ? (EPI & EPI_LN1) != 0 : g.ln1_gamma != nullptr;
   const bool F_RESID = EPI >= 0 ? (EPI & EPI_RESID) != 0 : g.resid != nullptr;
@@ -388,7 +405,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   const bool F_OACT = EPI >= 0 ? (EPI & EPI_OACT) != 0 : g.out_act != nullptr;
   const bool F_LN2 = EPI >= 0 ? (EPI & EPI_LN2) != 0 : g.ln2_gamma != nullptr;
   constexpr bool XB = EPI >= 0 && (EPI & EPI_XB) != 0;
-  constexpr int N_EPI_WARPS = EPI == EPI_OACT ? EPI_WARPS_MAX : EPI_WARPS;
+  // WLN: sixteen epilogue warps for the residual + LayerNorm kernels of the 16-bit stream (register-resident epilogue below)
+  constexpr int N_EPI_WARPS = (EPI == EPI_OACT || WLN) ? EPI_WARPS_MAX : EPI_WARPS;
   constexpr int N_SUB = N_EPI_WARPS / 4;  // warps sharing one TMEM lane quarter: they split the 32-column chunks of a tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -494,6 +512,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   // would block in setmaxnreg.inc for ever).  setmaxnreg sits inside the role branches so that ptxas allocates per role.
   if (warp < 4) {
   if (N_EPI_WARPS == EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  if (WLN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 128 x (96 - 56) freed >= 512 x (104 - 96) requested below
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -559,15 +578,25 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
+      long long* tr = p.trace ? p.trace + 8L * blockIdx.x : nullptr;
+      long long w_tempty = 0, w_full = 0, n_units = 0;
+      const long long t_begin = tr ? clock64() : 0;
+#define TC_TWAIT(counter, call)               \
+  do {                                        \
+    const long long c0_ = tr ? clock64() : 0; \
+    call;                                     \
+    if (tr) counter += clock64() - c0_;       \
+  } while (0)
       if (wres && unit0 < p.num_units) mbar_wait(wres_bar, 0, 6);
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
-        mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2);
+        ++n_units;
+        TC_TWAIT(w_tempty, mbar_wait(tempty_bar + 8 * acc_stage, acc_phase ^ 1, 2));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc_stage * p.acc_cols;
         if (p.slab) {
           const uint64_t* tab = reinterpret_cast<const uint64_t*>(smem_raw + (base - raw) + p.tab_off);
           for (int kb = 0; kb < k_blocks_per_tap; ++kb) {
-            mbar_wait(full_bar + 8 * stage, phase, 3);
+            TC_TWAIT(w_full, mbar_wait(full_bar + 8 * stage, phase, 3));
             tc_fence_after();
             const uint64_t a_stage_desc = make_smem_desc(smem_a + stage * p.a_stage_bytes);  // 1024-aligned: base offset 0
             for (int s = 0; s < g.n_taps; ++s) {
@@ -586,7 +615,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         }
         if constexpr (PAIR) {
           for (int it = 0; it < k_iters; ++it) {
-            mbar_wait(full_bar + 8 * stage, phase, 3);  // both CTAs' tiles of this stage have landed
+            TC_TWAIT(w_full, mbar_wait(full_bar + 8 * stage, phase, 3));  // both CTAs' tiles of this stage have landed
             tc_fence_after();
             const uint64_t adesc = make_smem_desc(smem_a + stage * p.a_stage_bytes);
             const uint64_t bdesc = make_smem_desc(smem_b + stage * p.b_stage_bytes);
@@ -600,7 +629,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
           continue;
         }
         for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(full_bar + 8 * stage, phase, 3);
+          TC_TWAIT(w_full, mbar_wait(full_bar + 8 * stage, phase, 3));
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_a + stage * p.a_stage_bytes);
           const uint64_t bdesc = make_smem_desc(smem_b + (wres ? it : stage) * p.b_stage_bytes);
@@ -617,10 +646,13 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         umma_commit(tfull_bar + 8 * acc_stage);  // accumulator complete -> epilogue
         if (++acc_stage == p.n_acc) { acc_stage = 0; acc_phase ^= 1; }
       }
+      if (tr) { tr[0] = clock64() - t_begin; tr[1] = w_tempty; tr[2] = w_full; tr[3] = n_units; }
+#undef TC_TWAIT
     }
   }
   } else {
     if (N_EPI_WARPS == EPI_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    if (WLN) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ===================== epilogue: every epilogue warp works on the current tile =====================
     // Warp e owns TMEM lane quarter q (rows q*32 .. q*32+31 of the tile) and the chunks c == sub_id (mod N_SUB), so a
     // row is shared by N_SUB threads; LayerNorm statistics are combined through smem + a named barrier per quarter.
@@ -629,7 +661,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     const int e = warp - 4;
     const int q = e & 3;        // TMEM lane quarter (warp index % 4)
     const int sub_id = e >> 2;  // which share of the column chunks
-    float* xch = reinterpret_cast<float*>(smem_raw + (bars + 512 - raw)) + q * (2 * 32 * 2);  // [2][32][2] for this quarter (LN kernels have N_SUB == 2)
+    float* xch = reinterpret_cast<float*>(smem_raw + (bars + 512 - raw)) + q * (4 * 32 * 2);  // [N_SUB <= 4][32][2] for this quarter
     auto row_sum2 = [&](float& a, float& b) {  // (a, b) summed over the N_SUB threads that share a row
       if (N_SUB == 1) return;
       xch[(sub_id * 32 + lane) * 2] = a;
@@ -663,6 +695,15 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     uint32_t n_out = 0;  // output chunks staged by this warp (alternates the bf16 staging buffers)
     const int n_chunks = p.block_n >> 5;
     const float* smf = reinterpret_cast<const float*>(smem_raw + (base - raw));
+    long long* etr = (p.trace && e == 0 && lane == 0) ? p.trace + 8L * blockIdx.x + 4 : nullptr;  // epilogue warp 0's view
+    long long ew_tfull = 0, ew_resid = 0;
+    const long long et_begin = etr ? clock64() : 0;
+#define TC_EWAIT(counter, call)                \
+  do {                                         \
+    const long long c0_ = etr ? clock64() : 0; \
+    call;                                      \
+    if (etr) counter += clock64() - c0_;       \
+  } while (0)
     for (int unit = unit0; unit < p.num_units; unit += unit_step, ++t_local) {
       if (tile_par && (t_local % N_SUB) != sub_id) {  // another share's tile: just keep the stage / phase counters in step
         if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
@@ -679,6 +720,152 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const float* v_b2 = p.vec_ln2 ? smf + p.vec_ln2 / 4 + p.block_n - n0 : g.ln2_beta;
       const float* v_act = g.act_vec ? (p.vec_act ? smf + p.vec_act / 4 - n0 : g.act_vec) : nullptr;
       const float* v_act2 = g.act2_vec ? (p.vec_act2 ? smf + p.vec_act2 / 4 - n0 : g.act2_vec) : nullptr;
+      constexpr bool EPI16_OK = WLN && XB && EPI >= 0 && (EPI & EPI_LN2) != 0 && (EPI & EPI_RESID) != 0 && N_SUB == 4;
+      constexpr int NCHK = 8 / N_SUB;  // 32-column chunks per thread: columns (sub_id + N_SUB * i) * 32
+      if (EPI16_OK && p.epi16) {
+        // ================= sixteen-warp epilogue (out-proj / FF2 / conv2 + residual + LayerNorm, 16-bit stream) =================
+        // tools/gemm_trace.py: with eight epilogue warps the epilogue of a tile takes 16 k clk (27 k with LN1 + Mish) against
+        // ~6-9 k for the tile's loads + MMAs, and ncu shows it is the warps' own instruction streams (~800-2000 instructions per
+        // thread and tile at 0.2 IPC per scheduler), not hand-offs.  Sixteen warps halve the stream per warp and double the
+        // warps per scheduler.  Same algorithm as the chunked path below (values stashed in TMEM between the two LayerNorm
+        // passes: keeping a thread's 64 values in registers spills at the 96-register budget of a 640-thread CTA, and with
+        // 227 KB of shared memory carved out a spill is an L2 round trip), but both residual chunks are in flight since before
+        // the accumulator wait and the residual buffers double as the staging of both outputs: 4 KB of staging per warp.
+        if (lane == 0) {
+          bulk_wait_read0();  // the previous tile's stores were staged in R
+          mbar_expect_tx(ebar, NCHK * EPI_B16_BYTES);
+#pragma unroll
+          for (int i = 0; i < NCHK; ++i) tma_load_2d(&tm.resid, ebar, sR + i * EPI_B16_BYTES, n0 + (sub_id + N_SUB * i) * 32, row0);
+        }
+        const int m = row0 + lane;
+        const long orow = (long)m * g.o_stride + g.o_off;
+        const bool in_range = m < g.M && orow < g.o_rows;
+        const int fr = (in_range && g.frame_row) ? g.frame_row[orow] : (in_range ? 0 : -1);
+        const bool row_valid = fr >= 0;
+        const float* add_row = (F_LN1 && g.add_row && row_valid) ? g.add_row + (long)g.row_tidx[fr] * g.add_row_stride : nullptr;
+        TC_EWAIT(ew_tfull, mbar_wait(tfull_bar + 8 * grp, acc_phase, 4));
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * p.acc_cols;
+        float mean1 = 0.f, rstd1 = 1.f;
+        if (F_LN1) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+          for (int i = 0; i < NCHK; ++i) {
+            const int c = sub_id + N_SUB * i;
+            uint32_t acc[32];
+            tmem_ld32(taddr + c * 32, acc);
+            float v[32];
+            acc_to_f32(acc, v);
+            if (v_bias) add_vec32(v, v_bias + n0 + c * 32, 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              s1 += v[j];
+              s2 = fmaf(v[j], v[j], s2);
+            }
+          }
+          row_sum2(s1, s2);
+          mean1 = s1 * (1.0f / 256.0f);
+          rstd1 = rsqrtf(fmaxf(s2 * (1.0f / 256.0f) - mean1 * mean1, 0.f) + 1e-5f);
+        }
+        float sum2 = 0.f, sq2 = 0.f, amax = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < NCHK; ++i) {
+          const int c = sub_id + N_SUB * i;
+          const int n = n0 + c * 32;
+          const uint32_t rbuf = sR + i * EPI_B16_BYTES;
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          float v[32];
+          acc_to_f32(acc, v);
+          if (v_bias) add_vec32(v, v_bias + n, 32);
+          if (F_LN1) ln_affine32(v, mean1, rstd1, v_g1 + n, v_b1 + n);
+          if (g.act != ACT_NONE) act32(v, g.act, g.act_param, v_act ? v_act + n : nullptr, 32);
+          if (add_row) add_vec32(v, add_row + n, 32);
+          if (!row_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (i == 0) {
+            TC_EWAIT(ew_resid, mbar_wait(ebar, ephase & 1, 5));
+            ephase ^= 1;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 r = lds128(rbuf + swz64(lane, j));
+            const uint32_t w[4] = {__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z), __float_as_uint(r.w)};
+            if (g.x_in_half) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+                v[8 * j + 2 * k] += f.x;
+                v[8 * j + 2 * k + 1] += f.y;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+                v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            acc[j] = __float_as_uint(v[j]);
+            sum2 += v[j];
+            sq2 = fmaf(v[j], v[j], sq2);
+            amax = fmaxf(amax, fabsf(v[j]));
+          }
+          tmem_st32(taddr + c * 32, acc);  // kept for the LayerNorm pass
+          // the stream value, rounded to fp16 (saturating) or bf16, over the residual chunk this lane has just read
+          if (g.x_out_half) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128u(rbuf + swz64(lane, j), pack_f16_sat(v[8 * j], v[8 * j + 1]), pack_f16_sat(v[8 * j + 2], v[8 * j + 3]),
+                      pack_f16_sat(v[8 * j + 4], v[8 * j + 5]), pack_f16_sat(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128u(rbuf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                      pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm.out_f32, rbuf, n, row0);
+            bulk_commit();
+          }
+        }
+        row_sum2(sum2, sq2);
+        if (g.x_out_half && g.sat_flag && amax >= 65504.f) atomicAdd(g.sat_flag, 1);
+        const float mean2 = sum2 * (1.0f / 256.0f);
+        const float rstd2 = rsqrtf(fmaxf(sq2 * (1.0f / 256.0f) - mean2 * mean2, 0.f) + 1e-5f);
+#pragma unroll 1
+        for (int i = 0; i < NCHK; ++i) {
+          const int c = sub_id + N_SUB * i;
+          const int n = n0 + c * 32;
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          float v[32];
+          acc_to_f32(acc, v);
+          ln_affine32(v, mean2, rstd2, v_g2 + n, v_b2 + n);
+          if (!row_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (lane == 0) bulk_wait_read1();  // the stream store of this chunk (two groups back at least) has read R[i]
+          __syncwarp();
+          stage_store_b16(&tm.out_ln, sR + i * EPI_B16_BYTES, lane, v, n, row0);
+        }
+        tc_fence_before();
+        if constexpr (PAIR) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(tempty_bar + 8 * grp, 0));
+        } else {
+          mbar_arrive(tempty_bar + 8 * grp);
+        }
+        if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
+        continue;
+      }
       if (XB) {  // residual of the first two chunks: in flight while the accumulator is still being computed
         if (lane == 0) {
           mbar_expect_tx(ebar, EPI_B16_BYTES);
@@ -701,7 +888,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const int fr = (in_range && g.frame_row) ? g.frame_row[orow] : (in_range ? 0 : -1);
       const bool row_valid = fr >= 0;
       const float* add_row = (F_LN1 && g.add_row && row_valid) ? g.add_row + (long)g.row_tidx[fr] * g.add_row_stride : nullptr;
-      mbar_wait(tfull_bar + 8 * grp, acc_phase, 4);
+      TC_EWAIT(ew_tfull, mbar_wait(tfull_bar + 8 * grp, acc_phase, 4));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * p.acc_cols;
 
@@ -752,7 +939,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
         }
         if (XB) {
           const int ib = i_chunk & 1;
-          mbar_wait(ebar + 8 * ib, (ephase >> ib) & 1, 5);
+          TC_EWAIT(ew_resid, mbar_wait(ebar + 8 * ib, (ephase >> ib) & 1, 5));
           ephase ^= 1u << ib;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -779,7 +966,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             tma_load_2d(&tm.resid, ebar + 8 * ib, sR + ib * EPI_B16_BYTES, n + 64 * c_step, row0);
           }
         } else if (F_RESID && !(p.debug & 512)) {
-          mbar_wait(ebar, ephase, 5);
+          TC_EWAIT(ew_resid, mbar_wait(ebar, ephase, 5));
           ephase ^= 1;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -884,6 +1071,8 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       }
       if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
     }
+    if (etr) { etr[0] = clock64() - et_begin; etr[1] = ew_tfull; etr[2] = ew_resid; etr[3] = t_local; }
+#undef TC_EWAIT
     if (lane == 0) bulk_wait0();  // smem must outlive the last TMA store's reads
   }
 
@@ -900,6 +1089,16 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 }  // namespace tc
 
 // ---------------------------------------------------------------- host side
+// development aid (tools/gemm_trace.py, jv_debug_gemm_trace): launches whose epilogue mask equals `epi` fill `buf`
+struct GemmTrace {
+  long long* buf = nullptr;
+  int epi = -1;
+};
+inline GemmTrace& gemm_trace() {
+  static GemmTrace t;
+  return t;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
