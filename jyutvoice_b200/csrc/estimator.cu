@@ -361,7 +361,8 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
     const bool to_copy = copy_to != nullptr;
     launch_mlp_fused(e.tmaps, c.b.LNX, w.ff1.W, w.ff1.bias, w.ff2.W, w.ff2.bias, c.b.X, to_copy ? copy_to : c.b.X, to_copy ? 0 : 1,
                      next_ln ? next_ln->g : nullptr, next_ln ? next_ln->b : nullptr, next_ln ? c.b.LNX : nullptr, c.b.frame_row,
-                     c.M_alloc, e.num_sms, 2.0 * (double)c.valid_frames * (2.0 * C * 1024), e.sat_flag, c.st);
+                     c.M_alloc, e.num_sms, 2.0 * (double)c.valid_frames * (2.0 * C * 1024), e.sat_flag, c.st, c.b.FF,
+                     (size_t)c.M_alloc * 1024 * e.act_size());  // FF (the unfused path's hidden activation) is free: tail scratch
     return;
   }
   g = conv_desc(c, w.ff1, c.b.LNX, nullptr, 1);

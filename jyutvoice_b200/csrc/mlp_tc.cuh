@@ -36,6 +36,13 @@ struct Params {
   int out_half;  // stream out is fp16 (else bf16: the copy that feeds the next conv)
   int* sat_flag; // fp16 stream: counts stores that reached +-65504 (see GemmDesc::sat_flag)
   long long* trace;  // debug: per-pair wait-time counters of the MMA thread (jv_debug_attention_trace buffer), or null
+  // Pair kernel, work items.  Whole mode (partial == 0): item = pair-tile pair_base + it, all 8 hidden chunks.  Partial mode
+  // (the tail of a launch whose pair-tiles do not fill the last wave): item = (pair-tile pair_base + it / 8, hidden chunk it % 8);
+  // the raw fp32 partial sum of the chunk's FF2 contribution goes to scratch[chunk][row - 256 * pair_base][256] and
+  // mlp_tail_finish_kernel adds the eight of them, the bias and the residual and applies the LayerNorm.
+  int pair_base, n_items, partial;
+  float* scratch;
+  long scratch_rows;  // rows per chunk plane of `scratch`
 };
 
 __global__ void __launch_bounds__(THREADS, 1) mlp_fused_kernel(const __grid_constant__ Maps tm, const Params p) {
@@ -433,7 +440,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
-  const int num_pairs = (p.num_tiles + 1) >> 1;
+  // item `it` -> pair-tile pt, first hidden chunk c0, number of chunks nc
+  auto item_pt = [&](int it) { return p.pair_base + (p.partial ? it / NCH : it); };
+  auto item_c0 = [&](int it) { return p.partial ? it % NCH : 0; };
+  const int nc = p.partial ? 1 : NCH;
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -463,16 +473,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
             ++wi;
           }
         };
-        for (int pt = pair0; pt < num_pairs; pt += pair_step, ++t_local) {
-          const int tile = 2 * pt + rank;
+        for (int it = pair0; it < p.n_items; it += pair_step, ++t_local) {
+          const int tile = 2 * item_pt(it) + rank, c0 = item_c0(it);
           mbar_wait(a_empty, (t_local & 1) ^ 1, 32);
           if (rank == 0) mbar_expect_tx(a_full, 2 * 4 * UNIT);
           for (int kb = 0; kb < 4; ++kb) tma_load_2d_cg2(&tm.a, a_full_l, sA + kb * UNIT, kb * 64, tile * BLOCK_M);
-          load_g1(0);
-          load_g1(1);
-          for (int c = 0; c < NCH; ++c) {
-            load_g2(c);
-            if (c + 2 < NCH) load_g1(c + 2);
+          load_g1(c0);
+          if (nc > 1) load_g1(c0 + 1);
+          for (int i = 0; i < nc; ++i) {
+            load_g2(c0 + i);
+            if (i + 2 < nc) load_g1(c0 + i + 2);
           }
         }
       }
@@ -494,7 +504,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
         uint32_t wi = 0, t_local = 0;
         uint32_t u1[2] = {0, 0};  // uses of acc1[b] / H[b]
         uint32_t uh[2] = {0, 0};
-        auto g1 = [&](int c) {
+        auto g1 = [&](int c) {  // c: index of the chunk within the item (buffer parity)
           const int b = c & 1;
           const long long g1_0 = tr ? clock64() : 0, g1_w0 = w_acc1e + w_wfull;
           MLP_TWAIT(w_acc1e, mbar_wait(acc1_empty + 8 * b, (u1[b] & 1) ^ 1, 33));
@@ -531,15 +541,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
           umma_commit_cg2(h_empty + 8 * b, 3);
           ++uh[b];
         };
-        for (int pt = pair0; pt < num_pairs; pt += pair_step, ++t_local) {
+        for (int it = pair0; it < p.n_items; it += pair_step, ++t_local) {
           MLP_TWAIT(w_afull, mbar_wait(a_full, t_local & 1, 38));
           tc_fence_after();
           g1(0);
-          g1(1);
-          for (int c = 0; c < NCH; ++c) {
+          if (nc > 1) g1(1);
+          if (nc <= 2) umma_commit_cg2(a_empty, 3);  // the item's last read of LNX has been issued
+          for (int c = 0; c < nc; ++c) {
             g2(c);
-            if (c + 2 < NCH) g1(c + 2);
-            if (c + 2 == NCH - 1) umma_commit_cg2(a_empty, 3);  // the pair's last read of LNX has been issued
+            if (c + 2 < nc) g1(c + 2);
+            if (nc > 2 && c + 2 == nc - 1) umma_commit_cg2(a_empty, 3);
           }
           umma_commit_cg2(acc2_full, 3);
         }
@@ -583,13 +594,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
     const uint32_t ebar = epi_bar + 16 * e;
     uint32_t u1[2] = {0, 0};
     uint32_t t_local = 0;
-    for (int pt = pair0; pt < num_pairs; pt += pair_step, ++t_local) {
-      const int tile = 2 * pt + rank;
+    for (int it = pair0; it < p.n_items; it += pair_step, ++t_local) {
+      const int tile = 2 * item_pt(it) + rank, c0 = item_c0(it);
       const int m0 = tile * BLOCK_M, row0 = m0 + q * 32;
       const int m = row0 + lane;
       const bool row_valid = m < p.M && p.frame_row[m] >= 0;
-      for (int c = 0; c < NCH; ++c) {
-        const int b = c & 1;
+      for (int ci = 0; ci < nc; ++ci) {
+        const int b = ci & 1, c = c0 + ci;
         mbar_wait(acc1_full + 8 * b, u1[b] & 1, 41);
         tc_fence_after();
         mbar_wait(h_empty + 8 * b, (u1[b] & 1) ^ 1, 42);
@@ -621,6 +632,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
       // ---- final epilogue: acc2 + b2 + residual -> stream out [-> LayerNorm out]; this warp's chunks: columns (sub + 4 i) * 32
       mbar_wait(acc2_full, t_local & 1, 43);
       tc_fence_after();
+      if (p.partial) {  // the chunk's raw contribution to the tile, fp32, to its plane of the scratch
+        const long srow = (long)m - 2L * p.pair_base * BLOCK_M;
+        float* dst = p.scratch + ((long)c0 * p.scratch_rows + srow) * C;
+#pragma unroll 1
+        for (int i = 0; i < 2; ++i) {
+          const int n = (sub + 4 * i) * 32;
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + lane_addr + 256 + n, acc);
+          if (srow < p.scratch_rows) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(dst + n + 4 * j) = make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(acc2_empty_l);
+        continue;
+      }
       if (lane == 0) {
         mbar_expect_tx(ebar, EPI_B16_BYTES);
         tma_load_2d(&tm.r, ebar, sStage, sub * 32, row0);
@@ -725,6 +755,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
   }
 }
 
+// Second half of the tail (see Params::partial): x' = sum of the eight partial planes + b2 + x, stored to the 16-bit stream
+// (or as the bf16 copy), and LayerNorm(x') as bf16.  One warp per row, eight channels per lane; same arithmetic order as the
+// fused epilogue (fp32 sum, one-sweep statistics).  768 rows at the benchmark's size: a few microseconds.
+__global__ void __launch_bounds__(256) mlp_tail_finish_kernel(const float* __restrict__ scratch, long scratch_rows, int row_base, int M,
+                                                              const int* __restrict__ frame_row, const float* __restrict__ b2,
+                                                              const uint16_t* __restrict__ x_in, uint16_t* __restrict__ out, int out_half,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              uint16_t* __restrict__ lnx_out, int* __restrict__ sat_flag) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int m = row_base + w;
+  if (w >= scratch_rows || m >= M) return;
+  const bool row_valid = frame_row[m] >= 0;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (row_valid) {
+    for (int c = 0; c < NCH; ++c) {
+      const float4* src = reinterpret_cast<const float4*>(scratch + ((long)c * scratch_rows + w) * C + lane * 8);
+      const float4 a = src[0], b = src[1];
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+      v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += b2[lane * 8 + j];
+  }
+  {  // residual: the 16-bit stream is fp16 here (the fused feed-forward runs on the fp16 stream only)
+    const uint4 r = *reinterpret_cast<const uint4*>(x_in + (long)m * C + lane * 8);
+    const uint32_t wv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&wv[k]));
+      v[2 * k] += f.x;
+      v[2 * k + 1] += f.y;
+    }
+  }
+  float sum = 0.f, sq = 0.f, amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sum += v[j];
+    sq = fmaf(v[j], v[j], sq);
+    amax = fmaxf(amax, fabsf(v[j]));
+  }
+  uint4 o;
+  if (out_half) {
+    o = make_uint4(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]), pack_f16_sat(v[4], v[5]), pack_f16_sat(v[6], v[7]));
+    if (sat_flag && amax >= 65504.f) atomicAdd(sat_flag, 1);
+  } else {
+    o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+  *reinterpret_cast<uint4*>(out + (long)m * C + lane * 8) = o;
+  if (gamma) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    }
+    const float mean = sum * (1.0f / C);
+    const float rstd = rsqrtf(fmaxf(sq * (1.0f / C) - mean * mean, 0.f) + 1e-5f);
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = row_valid ? fmaf((v[j] - mean) * rstd, gamma[lane * 8 + j], beta[lane * 8 + j]) : 0.f;
+    *reinterpret_cast<uint4*>(lnx_out + (long)m * C + lane * 8) =
+        make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+  }
+}
+
 }  // namespace mlp
 
 // JYUTVOICE_B200_MLP_PAIR=0: the single-CTA fused kernel instead of the CTA-pair one
@@ -742,7 +838,7 @@ static inline bool mlp_pair_mode() {
 static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const void* W1, const float* b1, const void* W2,
                                     const float* b2, const void* x_in, void* out, int out_half, const float* gamma,
                                     const float* beta, void* lnx_out, const int* frame_row, long M_alloc, int num_sms,
-                                    double algo_flops, int* sat_flag, cudaStream_t st) {
+                                    double algo_flops, int* sat_flag, cudaStream_t st, void* scratch = nullptr, size_t scratch_bytes = 0) {
   static unsigned long long attr = 0;
   if (first_use_on_device(attr)) {
     JV_CUDA(cudaFuncSetAttribute(mlp::mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
@@ -768,6 +864,31 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
   p.out_half = out_half;
   p.sat_flag = sat_flag;
   p.trace = attention_trace_buffer();
+  p.pair_base = 0;
+  p.n_items = (p.num_tiles + 1) / 2;
+  p.partial = 0;
+  p.scratch = nullptr;
+  p.scratch_rows = 0;
+  // Tail split: N pair-tiles on S pair slots run ceil(N / S) rounds, and with N = 151, S = 74 the third round holds 3 of
+  // them: 142 SMs idle for a whole tile time.  When the remainder r is small the launch is split: the first N - r pair-tiles
+  // as before (full rounds), then a second launch whose items are (tail pair-tile, hidden chunk) pairs, 8 r items of an
+  // eighth of a tile each, then a row kernel that sums the eight partial planes and finishes the epilogue.
+  int tail_pairs = 0;
+  if (pair) {
+    // Opt-in (JYUTVOICE_B200_MLP_TAIL=1): +1.9 % end to end at the benchmark's size, but the rows of the tail tiles then sum
+    // their eight chunk contributions in another order than the rows of whole tiles, so an utterance's result depends
+    // (within bf16 noise) on where it sits in the batch; the default keeps results bit-identical across batch compositions.
+    static const int tail_on = [] {
+      const char* e = getenv("JYUTVOICE_B200_MLP_TAIL");
+      return (e && e[0] == '1') ? 1 : 0;
+    }();
+    const int slots = num_sms / 2, n_pairs = p.n_items;
+    const int r = n_pairs % slots;
+    if (tail_on && n_pairs > slots && r > 0 && r * mlp::NCH <= slots && scratch &&
+        scratch_bytes >= (size_t)mlp::NCH * r * 2 * tc::BLOCK_M * mlp::C * sizeof(float) && !p.trace)
+      tail_pairs = r;
+  }
+  if (tail_pairs) p.n_items -= tail_pairs;
   ProfileState& ps = profile_state();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ps.on) {
@@ -779,7 +900,7 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
   memset(&cfg, 0, sizeof(cfg));
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
   if (pair) {
-    grid = 2 * std::min((p.num_tiles + 1) / 2, num_sms / 2);  // whole CTA pairs (the kernel carries __cluster_dims__(2,1,1))
+    grid = 2 * std::min(p.n_items, num_sms / 2);  // whole CTA pairs (the kernel carries __cluster_dims__(2,1,1))
   }
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(pair ? mlp::PAIR_THREADS : mlp::THREADS);
@@ -793,6 +914,22 @@ static inline void launch_mlp_fused(TmapCache& cache, const void* lnx_in, const 
   if (pair) JV_CUDA(cudaLaunchKernelEx(&cfg, mlp::mlp_fused_pair_kernel, tm, p));
   else JV_CUDA(cudaLaunchKernelEx(&cfg, mlp::mlp_fused_kernel, tm, p));
   JV_LAUNCHED();
+  if (tail_pairs) {
+    mlp::Params pt = p;
+    pt.pair_base = p.n_items;
+    pt.n_items = tail_pairs * mlp::NCH;
+    pt.partial = 1;
+    pt.scratch = (float*)scratch;
+    pt.scratch_rows = (long)tail_pairs * 2 * tc::BLOCK_M;
+    cfg.gridDim = dim3(2 * std::min(pt.n_items, num_sms / 2));
+    JV_CUDA(cudaLaunchKernelEx(&cfg, mlp::mlp_fused_pair_kernel, tm, pt));
+    JV_LAUNCHED();
+    const int row_base = pt.pair_base * 2 * tc::BLOCK_M;
+    mlp::mlp_tail_finish_kernel<<<cdiv((int)pt.scratch_rows * 32, 256), 256, 0, st>>>(
+        pt.scratch, pt.scratch_rows, row_base, p.M, frame_row, b2, (const uint16_t*)x_in, (uint16_t*)out, out_half, p.gamma, beta,
+        (uint16_t*)lnx_out, sat_flag);
+    JV_LAUNCHED();
+  }
   if (ps.on) {
     JV_CUDA(cudaEventRecord(e1, st));
     ps.ev.push_back(e0);

@@ -269,6 +269,41 @@ def test_fused_mlp_experimental_path():
     assert err <= BF16_MEL_TOL and rel <= BF16_MEL_RELRMS
 
 
+def test_mlp_tail_split_experimental_path(tmp_path):
+    """JYUTVOICE_B200_MLP_TAIL=1 (opt-in): the pair-tiles that do not fill the last wave of the fused feed-forward are
+    split by hidden chunk over all SMs and summed by a row kernel.  Not bit-identical to the default (another summation
+    order for those rows), so: the path is taken (more launches), the result is finite and within bf16 noise of the default."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "from jyutvoice_b200 import CausalConditionalCFM, CausalConditionalDecoder, synthetic, _lib\n"
+        "cfm = CausalConditionalCFM(estimator=CausalConditionalDecoder(precision='bf16'))\n"
+        "cfm.load_state_dict(synthetic.make_estimator_state_dict(), strict=True)\n"
+        "cfm = cfm.cuda()\n"
+        "g = torch.Generator().manual_seed(9)\n"
+        "lens = [int(v) for v in torch.randint(270, 331, (64,), generator=g)]\n"
+        "mu = torch.randn(64, 80, 330, generator=g).cuda(); spks = torch.randn(64, 80, generator=g).cuda()\n"
+        "n0 = _lib.lib().jv_launch_count()\n"
+        "mel, _ = cfm(mu, None, 2, 1.0, spks, None, lengths=lens)\n"
+        "torch.cuda.synchronize()\n"
+        "np.save(sys.argv[1], mel.cpu().numpy())\n"
+        "print('LAUNCHES', _lib.lib().jv_launch_count() - n0)\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mels, launches = [], []
+    for tail in ("0", "1"):
+        env = dict(os.environ, JYUTVOICE_B200_MLP_TAIL=tail, JYUTVOICE_B200_GRAPH="0", PYTHONPATH=root)
+        f = str(tmp_path / f"mel{tail}.npy")
+        out = subprocess.run([sys.executable, "-c", code, f], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        mels.append(torch.from_numpy(np.load(f)))
+        launches.append(int(out.stdout.split("LAUNCHES")[1].split()[0]))
+    assert launches[1] == launches[0] + 2 * 2 * 56      # two extra launches per fused feed-forward, 56 blocks, 2 NFE
+    assert torch.isfinite(mels[1]).all()
+    assert (mels[0] - mels[1]).abs().max().item() <= BF16_MEL_TOL and rel_rms(mels[1], mels[0]) <= BF16_MEL_RELRMS
+
+
 def test_cfm_solve_replays_a_graph_and_matches_eager_counts(cfms):
     """Steps 1 .. n-1 of a solve replay one captured Euler step; the kernel-launch counter stays what eager gives."""
     from jyutvoice_b200 import _lib
