@@ -72,8 +72,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int r = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
   const int len = row_len[r];
   // optional per-CTA timeline (jv_debug_attention_trace): 8 clock64 values written by thread 0 (softmax warp 0)
+  // (only in -DJV_TRACE builds: the run-time flag around the waits costs a few per cent)
+#ifdef JV_TRACE
   long long* tr = trace ? trace + 8L * ((long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   const bool tracer = tr != nullptr && threadIdx.x == 0;
+#else
+  constexpr long long* tr = nullptr;
+  constexpr bool tracer = false;
+#endif
   long long w_s = 0, w_o = 0;
   if (tracer) tr[0] = clock64();
   if (q0 >= len) return;

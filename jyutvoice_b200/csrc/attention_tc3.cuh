@@ -92,7 +92,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const int* __restrict__ row_off, const int* __restrict__ row_len, const int* __restrict__ items, int n_items,
                      float scale_log2e, int chunk, long long* __restrict__ trace) {
   // optional per-CTA timeline (jv_debug_attention_trace): sums over the CTA's items, written by thread 0 (softmax warp 0)
+#ifdef JV_TRACE
   long long* tr = trace ? trace + 16L * blockIdx.x : nullptr;
+#else
+  constexpr long long* tr = nullptr;
+#endif
   const bool tracer = tr != nullptr && threadIdx.x == 0;
   long long t_decode = 0, t_first_s = 0, t_loop = 0, t_wait_s = 0, t_wait_o = 0, t_final = 0, t_store = 0;
   const long long t_entry = tracer ? clock64() : 0;

@@ -388,6 +388,14 @@ __device__ __forceinline__ void stage_store_b16(const CUtensorMap* tm, uint32_t 
 
 // EPI: compile-time epilogue feature mask (specialised instantiations keep the per-chunk instruction stream short);
 // EPI < 0 is the generic kernel that tests the descriptor at run time.
+// Bisecting aids (JYUTVOICE_B200_DEBUG bit mask, the wait-time counters of tools/gemm_trace.py / mlp_trace.py /
+// attention_trace.py) exist only in builds with -DJV_TRACE: as run-time flags inside the epilogue and MMA loops they cost
+// 3.5-4.5 % end to end (same-box A/B: 156.2 vs 149.3-150.8 ms per step).
+#ifdef JV_TRACE
+#define JV_DBG(p) ((p).debug)
+#else
+#define JV_DBG(p) 0
+#endif
 constexpr int EPI_LN1 = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_OACT = 8, EPI_LN2 = 16;
 // EPI_XB: the residual stream is bf16 (GemmDesc::x_bf16): `resid` in and the main output are 2 KB bf16 chunks, so the
 // same 8 KB of staging per warp holds two residual chunks in flight and two output buffers (no store is ever waited for
@@ -578,7 +586,13 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       uint32_t phase = 0;
       int acc_stage = 0;
       uint32_t acc_phase = 0;
+      // wait-time counters: only in builds with -DJV_TRACE (JYUTVOICE_B200_NVCC_FLAGS=-DJV_TRACE python -m jyutvoice_b200.build --force);
+      // a run-time flag around every wait of this single-thread loop is not free
+#ifdef JV_TRACE
       long long* tr = p.trace ? p.trace + 8L * blockIdx.x : nullptr;
+#else
+      constexpr long long* tr = nullptr;
+#endif
       long long w_tempty = 0, w_full = 0, n_units = 0;
       const long long t_begin = tr ? clock64() : 0;
 #define TC_TWAIT(counter, call)               \
@@ -695,7 +709,11 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
     uint32_t n_out = 0;  // output chunks staged by this warp (alternates the bf16 staging buffers)
     const int n_chunks = p.block_n >> 5;
     const float* smf = reinterpret_cast<const float*>(smem_raw + (base - raw));
+#ifdef JV_TRACE
     long long* etr = (p.trace && e == 0 && lane == 0) ? p.trace + 8L * blockIdx.x + 4 : nullptr;  // epilogue warp 0's view
+#else
+    constexpr long long* etr = nullptr;
+#endif
     long long ew_tfull = 0, ew_resid = 0;
     const long long et_begin = etr ? clock64() : 0;
 #define TC_EWAIT(counter, call)                \
@@ -875,7 +893,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             tma_load_2d(&tm.resid, ebar + 8, sR + EPI_B16_BYTES, n0 + (c_first + c_step) * 32, row0);
           }
         }
-      } else if (F_RESID && lane == 0 && !(p.debug & 512)) {  // residual of the first chunk: in flight while the accumulator is still being computed
+      } else if (F_RESID && lane == 0 && !(JV_DBG(p) & 512)) {  // residual of the first chunk: in flight while the accumulator is still being computed
         if (F_LN2) bulk_wait_read0();  // the previous tile's post-LayerNorm stores may still be reading R
         mbar_expect_tx(ebar, EPI_F32_BYTES);
         tma_load_2d(&tm.resid, ebar, sR, n0 + c_first * 32, row0);
@@ -894,7 +912,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
 
       // ---- optional pre-LayerNorm statistics of (acc + bias) over the whole row (block_n == N == 256)
       float mean1 = 0.f, rstd1 = 1.f;
-      if (F_LN1 && !(p.debug & 32)) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
+      if (F_LN1 && !(JV_DBG(p) & 32)) {  // one sweep: sum and sum of squares in fp32 (256 O(1) values; bf16-mode tolerance)
         float s1 = 0.f, s2 = 0.f;
         for (int c = c_first; c < n_chunks; c += c_step) {
           uint32_t acc[32];
@@ -918,20 +936,20 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       float amax = 0.f;  // largest |value| this thread stores into the 16-bit stream (saturation counter)
       const int n_chunks_valid = (g.N - n0 + 31) / 32 < n_chunks ? (g.N - n0 + 31) / 32 : n_chunks;
       int i_chunk = 0;
-      for (int c = c_first; c < ((p.debug & 2) ? 0 : n_chunks_valid); c += c_step, ++i_chunk) {
+      for (int c = c_first; c < ((JV_DBG(p) & 2) ? 0 : n_chunks_valid); c += c_step, ++i_chunk) {
         const int n = n0 + c * 32;
         const int n_valid = g.N - n < 32 ? g.N - n : 32;
         uint32_t acc[32];
         tmem_ld32(taddr + c * 32, acc);
         float v[32];
         acc_to_f32(acc, v);
-        if (p.debug & 4) {  // experiment: TMEM reads only
+        if (JV_DBG(p) & 4) {  // experiment: TMEM reads only
           if (v[0] == 123.456f) printf("x");
           continue;
         }
-        if (v_bias && !(p.debug & 8)) add_vec32(v, v_bias + n, n_valid);
-        if (F_LN1 && !(p.debug & 128)) ln_affine32(v, mean1, rstd1, v_g1 + n, v_b1 + n);
-        if (g.act != ACT_NONE && !(p.debug & 64)) act32(v, g.act, g.act_param, v_act ? v_act + n : nullptr, n_valid);
+        if (v_bias && !(JV_DBG(p) & 8)) add_vec32(v, v_bias + n, n_valid);
+        if (F_LN1 && !(JV_DBG(p) & 128)) ln_affine32(v, mean1, rstd1, v_g1 + n, v_b1 + n);
+        if (g.act != ACT_NONE && !(JV_DBG(p) & 64)) act32(v, g.act, g.act_param, v_act ? v_act + n : nullptr, n_valid);
         if (add_row) add_vec32(v, add_row + n, n_valid);
         if (!row_valid) {
 #pragma unroll
@@ -965,7 +983,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             mbar_expect_tx(ebar + 8 * ib, EPI_B16_BYTES);
             tma_load_2d(&tm.resid, ebar + 8 * ib, sR + ib * EPI_B16_BYTES, n + 64 * c_step, row0);
           }
-        } else if (F_RESID && !(p.debug & 512)) {
+        } else if (F_RESID && !(JV_DBG(p) & 512)) {
           TC_EWAIT(ew_resid, mbar_wait(ebar, ephase, 5));
           ephase ^= 1;
 #pragma unroll
@@ -1020,9 +1038,9 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
             sts128u(hbuf + swz64(lane, j), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                     pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         }
-        if (!(p.debug & 16)) fence_async_smem();
+        if (!(JV_DBG(p) & 16)) fence_async_smem();
         __syncwarp();
-        if (lane == 0 && !(p.debug & 1)) {
+        if (lane == 0 && !(JV_DBG(p) & 1)) {
           if (XB) tma_store_2d(&tm.out_f32, hbuf, n, row0);
           else if (F_F32) tma_store_2d(&tm.out_f32, sOF, n, row0);
           if (F_OACT) tma_store_2d(&tm.out_act, hbuf, n, row0);

@@ -493,7 +493,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
       // ===================== MMA issuer (leader CTA only) =====================
       if (lane == 0 && rank == 0) {
         // optional trace (jv_debug_attention_trace buffer): cycles the MMA thread spends waiting, per barrier kind
+#ifdef JV_TRACE
         long long* tr = p.trace ? p.trace + 8L * (blockIdx.x >> 1) : nullptr;
+#else
+        constexpr long long* tr = nullptr;  // (tools/mlp_trace.py needs a -DJV_TRACE build)
+#endif
         long long w_acc1e = 0, w_wfull = 0, w_hfull = 0, w_acc2e = 0, w_afull = 0, t_g1 = 0;  // t_g1: all of g1 incl. its waits
         const long long t_begin = tr ? clock64() : 0;
 #define MLP_TWAIT(counter, call)                \

@@ -1,4 +1,5 @@
-"""Per-CTA timeline of attention_tc2_kernel (clock64 stamps written by thread 0 of every CTA of ONE launch).
+"""[needs a tracing build: JYUTVOICE_B200_NVCC_FLAGS=-DJV_TRACE python -m jyutvoice_b200.build --force]
+Per-CTA timeline of attention_tc2_kernel (clock64 stamps written by thread 0 of every CTA of ONE launch).
 usage: python tools/attention_trace.py [batch=64] [frames=300]"""
 import ctypes, os, sys
 import torch

@@ -1,4 +1,5 @@
-"""Where the MMA thread and epilogue warp 0 of gemm_taps_tc_kernel wait, for the launches with one epilogue mask
+"""[needs a tracing build: JYUTVOICE_B200_NVCC_FLAGS=-DJV_TRACE python -m jyutvoice_b200.build --force]
+Where the MMA thread and epilogue warp 0 of gemm_taps_tc_kernel wait, for the launches with one epilogue mask
 (clock64 sums per CTA, last such launch of one estimator forward).
 usage: python tools/gemm_trace.py <epi mask, e.g. 54 = out-proj, 55 = conv2, 8 = QKV / FF1> [batch=64] [frames=300]"""
 import ctypes, os, sys

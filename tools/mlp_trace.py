@@ -1,4 +1,5 @@
-"""Where the MMA thread of mlp_fused_pair_kernel waits (clock64 sums per CTA pair, last launch of one estimator forward).
+"""[needs a tracing build: JYUTVOICE_B200_NVCC_FLAGS=-DJV_TRACE python -m jyutvoice_b200.build --force]
+Where the MMA thread of mlp_fused_pair_kernel waits (clock64 sums per CTA pair, last launch of one estimator forward).
 usage: python tools/mlp_trace.py [batch=64] [frames=300]"""
 import ctypes, os, sys
 import torch
