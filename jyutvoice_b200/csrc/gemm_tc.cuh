@@ -520,7 +520,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
   // would block in setmaxnreg.inc for ever).  setmaxnreg sits inside the role branches so that ptxas allocates per role.
   if (warp < 4) {
   if (N_EPI_WARPS == EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-  if (WLN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 128 x (96 - 56) freed >= 512 x (104 - 96) requested below
+  if (WLN) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");  // 128 x (96 - 64) freed = 512 x (104 - 96) requested below
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -740,7 +740,7 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const float* v_act2 = g.act2_vec ? (p.vec_act2 ? smf + p.vec_act2 / 4 - n0 : g.act2_vec) : nullptr;
       constexpr bool EPI16_OK = WLN && XB && EPI >= 0 && (EPI & EPI_LN2) != 0 && (EPI & EPI_RESID) != 0 && N_SUB == 4;
       constexpr int NCHK = 8 / N_SUB;  // 32-column chunks per thread: columns (sub_id + N_SUB * i) * 32
-      if (EPI16_OK && p.epi16) {
+      if constexpr (EPI16_OK) {  // (WLN instantiations are only launched for these kernels: TcParams::epi16)
         // ================= sixteen-warp epilogue (out-proj / FF2 / conv2 + residual + LayerNorm, 16-bit stream) =================
         // tools/gemm_trace.py: with eight epilogue warps the epilogue of a tile takes 16 k clk (27 k with LN1 + Mish) against
         // ~6-9 k for the tile's loads + MMAs, and ncu shows it is the warps' own instruction streams (~800-2000 instructions per

@@ -449,7 +449,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
   constexpr int nc = PARTIAL ? 1 : NCH;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
       // ===================== TMA producer (both CTAs) =====================
       if (lane == 0) {
@@ -509,12 +509,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
         const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M 256, N 128
         const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M 256, N 256
         uint32_t wi = 0, t_local = 0;
-        uint32_t u1[2] = {0, 0};  // uses of acc1[b] / H[b]
-        uint32_t uh[2] = {0, 0};
+        // phase parities of acc1[b] / H[b] as bit b of a scalar: a two-element array indexed by `b` lives in local
+        // memory, and this thread's waits would each start with a load from it
+        uint32_t par1 = 0, parh = 0;
         auto g1 = [&](int c) {  // c: index of the chunk within the item (buffer parity)
           const int b = c & 1;
           const long long g1_0 = tr ? clock64() : 0, g1_w0 = w_acc1e + w_wfull;
-          MLP_TWAIT(w_acc1e, mbar_wait(acc1_empty + 8 * b, (u1[b] & 1) ^ 1, 33));
+          MLP_TWAIT(w_acc1e, mbar_wait(acc1_empty + 8 * b, ((par1 >> b) & 1) ^ 1, 33));
           tc_fence_after();
           for (int s2 = 0; s2 < 2; ++s2, ++wi) {
             const uint32_t slot = wi % RW;
@@ -528,12 +529,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
             umma_commit_cg2(w_empty + 8 * slot, 3);
           }
           umma_commit_cg2(acc1_full + 8 * b, 3);
-          ++u1[b];
+          par1 ^= 1u << b;
           if (tr) t_g1 += (clock64() - g1_0) - (w_acc1e + w_wfull - g1_w0);  // issue time of the 16 MMAs + 3 commits, waits excluded
         };
         auto g2 = [&](int c) {
           const int b = c & 1;
-          MLP_TWAIT(w_hfull, mbar_wait(h_full + 8 * b, uh[b] & 1, 35));
+          MLP_TWAIT(w_hfull, mbar_wait(h_full + 8 * b, (parh >> b) & 1, 35));
           if (c == 0) MLP_TWAIT(w_acc2e, mbar_wait(acc2_empty, (t_local & 1) ^ 1, 36));
           tc_fence_after();
           for (int kb2 = 0; kb2 < 2; ++kb2, ++wi) {
@@ -546,7 +547,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
             umma_commit_cg2(w_empty + 8 * slot, 3);
           }
           umma_commit_cg2(h_empty + 8 * b, 3);
-          ++uh[b];
+          parh ^= 1u << b;
         };
         for (int it = pair0; it < p.n_items; it += pair_step, ++t_local) {
           MLP_TWAIT(w_afull, mbar_wait(a_full, t_local & 1, 38));
@@ -568,7 +569,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
       }
     }
   } else {
-    // register pool of the CTA = 640 threads x 96 (the compiled cap): 128 x (96 - 56) freed >= 512 x (104 - 96) requested.
+    // register pool of the CTA = 640 threads x 96 (the compiled cap): 128 x (96 - 64) freed = 512 x (104 - 96) requested.
     // (A larger request blocks in setmaxnreg.inc for ever.)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ===================== epilogue warps (both CTAs, each on its own 128 rows) =====================
@@ -599,7 +600,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
     // 2 x 2 KB... one per output chunk of this warp) -- outputs reuse the residual buffer of the same chunk once it is read
     const uint32_t sStage = sH + e * 4096;
     const uint32_t ebar = epi_bar + 16 * e;
-    uint32_t u1[2] = {0, 0};
+    uint32_t par1 = 0;  // phase parity of acc1[b] / H[b] in bit b
     uint32_t t_local = 0;
     for (int it = pair0; it < p.n_items; it += pair_step, ++t_local) {
       const int tile = 2 * item_pt(it) + rank, c0 = item_c0(it);
@@ -608,10 +609,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) mlp
       const bool row_valid = m < p.M && p.frame_row[m] >= 0;
       for (int ci = 0; ci < nc; ++ci) {
         const int b = ci & 1, c = c0 + ci;
-        mbar_wait(acc1_full + 8 * b, u1[b] & 1, 41);
+        mbar_wait(acc1_full + 8 * b, (par1 >> b) & 1, 41);
         tc_fence_after();
-        mbar_wait(h_empty + 8 * b, (u1[b] & 1) ^ 1, 42);
-        ++u1[b];
+        mbar_wait(h_empty + 8 * b, ((par1 >> b) & 1) ^ 1, 42);
+        par1 ^= 1u << b;
         uint32_t a0[32];
         tmem_ld32(tmem_base + lane_addr + b * NC + sub * 32, a0);
         tc_fence_before();
