@@ -82,7 +82,8 @@ static const KernelEntry* kernel_table() {
       {EPI_OACT, gemm_taps_tc_kernel<EPI_OACT>, gemm_taps_tc_kernel<EPI_OACT, true>},                                              // QKV, FF1, plain convs
       {EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_LN2, true>},    // out-proj, FF2 (+ next norm)
       {EPI_RESID | EPI_F32 | EPI_OACT, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_OACT>, gemm_taps_tc_kernel<EPI_RESID | EPI_F32 | EPI_OACT, true>},  // last FF2 of a group, HiFT conv2
-      {EPI_LN1 | EPI_OACT, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT>, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT, true>},                          // CausalBlock1D (block1, final_block)
+      {EPI_LN1 | EPI_OACT, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT>, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT, true>,                           // CausalBlock1D (block1, final_block)
+       gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT, false, true>, gemm_taps_tc_kernel<EPI_LN1 | EPI_OACT, true, true>},
       {EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, gemm_taps_tc_kernel<EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2>, gemm_taps_tc_kernel<EPI_LN1 | EPI_RESID | EPI_F32 | EPI_LN2, true>},  // block2 + res + norm1
       {EPI_F32, gemm_taps_tc_kernel<EPI_F32>, gemm_taps_tc_kernel<EPI_F32, true>},                                                // res_conv, final_proj, conv_post
       {EPI_RESID | EPI_F32, gemm_taps_tc_kernel<EPI_RESID | EPI_F32>, gemm_taps_tc_kernel<EPI_RESID | EPI_F32, true>},                        // HiFT ups + source, last conv2
@@ -247,7 +248,8 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
                ? 1
                : 0;
   if (p.pair) p.b_stage_bytes = round_up((p.block_n / 2) * tc::BLOCK_K * 2, 1024);
-  const bool epi16 = g.x_bf16 && g.resid && g.ln2_gamma && g.N == 256 && p.block_n == 256 && use_epi16();
+  const bool epi16 = ((g.x_bf16 && g.resid && g.ln2_gamma) || (epi == (tc::EPI_LN1 | tc::EPI_OACT) && !p.wres && !p.slab)) && g.N == 256 &&
+                     p.block_n == 256 && use_epi16();
   const bool wide = epi == tc::EPI_OACT || epi16;  // 16 epilogue warps, small staging: bf16-only epilogues and the sixteen-warp LayerNorm epilogue
   const int n_epi_warps = wide ? tc::EPI_WARPS_MAX : tc::EPI_WARPS;
   {  // staging layout per epilogue warp, exactly what this epilogue kind needs
@@ -255,8 +257,9 @@ void launch_gemm_tc(const GemmDesc& g, TmapCache& cache, int num_sms, cudaStream
     int off = 0;
     p.off_R = 0;
     p.epi16 = epi16 ? 1 : 0;
-    if (p.epi16) {  // sixteen warps: R0 R1 (residual in, stream out, LayerNorm out), 2 KB each
-      p.off_OF = p.off_OB = 0;
+    if (p.epi16) {  // sixteen warps: two 2 KB buffers (residual in / stream out / LayerNorm out, or two alternating bf16 outputs)
+      p.off_OF = 0;
+      p.off_OB = tc::EPI_B16_BYTES;
       off = 2 * tc::EPI_B16_BYTES;
     } else if (g.x_bf16) {  // R0 R1 | O0 | O1, 2 KB each
       p.off_OF = 2 * tc::EPI_B16_BYTES;

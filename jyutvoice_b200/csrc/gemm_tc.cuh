@@ -743,6 +743,69 @@ gemm_taps_tc_kernel(const __grid_constant__ TcMaps tm, const GemmDesc g, const T
       const float* v_act2 = g.act2_vec ? (p.vec_act2 ? smf + p.vec_act2 / 4 - n0 : g.act2_vec) : nullptr;
       constexpr bool EPI16_OK = WLN && XB && EPI >= 0 && (EPI & EPI_LN2) != 0 && (EPI & EPI_RESID) != 0 && N_SUB == 4;
       constexpr int NCHK = 8 / N_SUB;  // 32-column chunks per thread: columns (sub_id + N_SUB * i) * 32
+      if constexpr (WLN && EPI == (EPI_LN1 | EPI_OACT)) {
+        // ================= sixteen-warp epilogue of conv + LayerNorm + activation -> bf16 (CausalBlock1D) =================
+        // K = 3 x 256 gives 9 k clk of MMAs per tile and the eight-warp epilogue took 15.7 k (tools/gemm_trace.py): same remedy
+        // as below.  Statistics sweep, then the main pass; the two bf16 staging buffers alternate.
+        const int m = row0 + lane;
+        const long orow = (long)m * g.o_stride + g.o_off;
+        const bool in_range = m < g.M && orow < g.o_rows;
+        const int fr = (in_range && g.frame_row) ? g.frame_row[orow] : (in_range ? 0 : -1);
+        const bool row_valid = fr >= 0;
+        const float* add_row = (g.add_row && row_valid) ? g.add_row + (long)g.row_tidx[fr] * g.add_row_stride : nullptr;
+        TC_EWAIT(ew_tfull, mbar_wait(tfull_bar + 8 * grp, acc_phase, 4));
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * p.acc_cols;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < NCHK; ++i) {
+          const int c = sub_id + N_SUB * i;
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          float v[32];
+          acc_to_f32(acc, v);
+          if (v_bias) add_vec32(v, v_bias + n0 + c * 32, 32);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            s1 += v[j];
+            s2 = fmaf(v[j], v[j], s2);
+          }
+        }
+        row_sum2(s1, s2);
+        const float mean1 = s1 * (1.0f / 256.0f);
+        const float rstd1 = rsqrtf(fmaxf(s2 * (1.0f / 256.0f) - mean1 * mean1, 0.f) + 1e-5f);
+#pragma unroll 1
+        for (int i = 0; i < NCHK; ++i) {
+          const int c = sub_id + N_SUB * i;
+          const int n = n0 + c * 32;
+          uint32_t acc[32];
+          tmem_ld32(taddr + c * 32, acc);
+          float v[32];
+          acc_to_f32(acc, v);
+          if (v_bias) add_vec32(v, v_bias + n, 32);
+          ln_affine32(v, mean1, rstd1, v_g1 + n, v_b1 + n);
+          if (g.act != ACT_NONE) act32(v, g.act, g.act_param, v_act ? v_act + n : nullptr, 32);
+          if (add_row) add_vec32(v, add_row + n, 32);
+          if (!row_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (g.act2 != ACT_NONE) act32(v, g.act2, g.act2_param, v_act2 ? v_act2 + n : nullptr, 32);
+          if (lane == 0) bulk_wait_read1();  // the store that last used this buffer (two groups back) has read it
+          __syncwarp();
+          stage_store_b16(&tm.out_act, (n_out & 1) ? sOB : sOF, lane, v, n, row0);
+          ++n_out;
+        }
+        tc_fence_before();
+        if constexpr (PAIR) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(tempty_bar + 8 * grp, 0));
+        } else {
+          mbar_arrive(tempty_bar + 8 * grp);
+        }
+        if (++grp == p.n_acc) { grp = 0; acc_phase ^= 1; }
+        continue;
+      }
       if constexpr (EPI16_OK) {  // (WLN instantiations are only launched for these kernels: TcParams::epi16)
         // ================= sixteen-warp epilogue (out-proj / FF2 / conv2 + residual + LayerNorm, 16-bit stream) =================
         // tools/gemm_trace.py: with eight epilogue warps the epilogue of a tile takes 16 k clk (27 k with LN1 + Mish) against
