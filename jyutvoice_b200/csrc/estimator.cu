@@ -357,7 +357,10 @@ static void run_tblock(const FwdCtx& c, const TBlockW& w, const LNW* next_ln, vo
   g.x_in_half = g.x_out_half = c.h->stream_half();
   set_ln2(c, g, w.n3);
   e.gemm(g, c.st);
-  if (c.h->stream_half() && use_mlp_fused()) {  // FF1 + GELU + FF2 + residual (+ next norm1) in one kernel: the hidden never leaves the SM
+  // FF1 + GELU + FF2 + residual (+ next norm1) in one kernel: the hidden never leaves the SM.  Not for a handful of tiles: a
+  // tile streams the layer's 1 MB of weights through one SM pair's 5-slot ring (30 us at batch 1), where FF1 spreads its
+  // weight tiles over several CTAs (tools/latency_probe.py: 2 tiles 37.6 vs 39.0 ms per utterance, 10 tiles 46.9 vs 45.3)
+  if (c.h->stream_half() && use_mlp_fused() && (c.M_alloc > 4 * 128 || force_modes())) {
     const bool to_copy = copy_to != nullptr;
     launch_mlp_fused(e.tmaps, c.b.LNX, w.ff1.W, w.ff1.bias, w.ff2.W, w.ff2.bias, c.b.X, to_copy ? copy_to : c.b.X, to_copy ? 0 : 1,
                      next_ln ? next_ln->g : nullptr, next_ln ? next_ln->b : nullptr, next_ln ? c.b.LNX : nullptr, c.b.frame_row,

@@ -262,7 +262,7 @@ def test_fused_mlp_experimental_path():
         "print('ERR', float((v - ref).abs().max()), float((v - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()))\n"
     )
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, JYUTVOICE_B200_MLP="1", PYTHONPATH=root)
+    env = dict(os.environ, JYUTVOICE_B200_MLP="1", JYUTVOICE_B200_FORCE_MODES="1", PYTHONPATH=root)  # (small input: force the fused kernel)
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     err, rel = [float(z) for z in out.stdout.split("ERR")[1].split()[:2]]

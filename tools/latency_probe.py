@@ -7,7 +7,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = [{}, {"JYUTVOICE_B200_MLP": "0"}, {"JYUTVOICE_B200_PAIR": "0"}, {"JYUTVOICE_B200_MLP": "0", "JYUTVOICE_B200_PAIR": "0"},
-            {"JYUTVOICE_B200_ATTN_NCH": "3"}, {"JYUTVOICE_B200_GRAPH": "0"}, {"JYUTVOICE_B200_WRES": "0"}, {"JYUTVOICE_B200_PDL": "0"}]
+            {"JYUTVOICE_B200_ATTN_NCH": "3"}, {"JYUTVOICE_B200_GRAPH": "0"}, {"JYUTVOICE_B200_WRES": "0"}, {"JYUTVOICE_B200_PDL": "0"},
+            {"JYUTVOICE_B200_EPI16": "0"}, {"JYUTVOICE_B200_MLP": "0", "JYUTVOICE_B200_EPI16": "0"}]
+if os.environ.get("LATENCY_PROBE_VARIANTS"):  # e.g. "0,1,8,9"
+    VARIANTS = [VARIANTS[int(i)] for i in os.environ["LATENCY_PROBE_VARIANTS"].split(",")]
 
 if len(sys.argv) > 1 and sys.argv[1] == "--child":
     sys.path.insert(0, ROOT)
