@@ -69,7 +69,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      long long* __restrict__ trace) {
   constexpr int TK = Shape<NCH>::TK, KV_BYTES = Shape<NCH>::KV_BYTES, OFF_K = Shape<NCH>::OFF_K, OFF_V = Shape<NCH>::OFF_V,
                 OFF_BAR = Shape<NCH>::OFF_BAR, TMEM_COLS = Shape<NCH>::TMEM_COLS;
-  const int r = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
+  // rows in reverse order: the QKV GEMM has just written 119 MB (about the size of L2) in increasing row order, so the LAST rows
+  // are the ones still in L2 when this kernel starts
+  const int r = gridDim.z - 1 - blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
   const int len = row_len[r];
   // optional per-CTA timeline (jv_debug_attention_trace): 8 clock64 values written by thread 0 (softmax warp 0)
   // (only in -DJV_TRACE builds: the run-time flag around the waits costs a few per cent)
